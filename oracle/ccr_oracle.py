@@ -1,0 +1,332 @@
+"""CPU oracle for CCR's candidate score-and-rank path.  TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this module -- and there only as the checker or as
+the timed *reference* arm, never as the product path.  The product
+(``ccr_b200``) never imports it and fails loudly when the CUDA library is missing.
+
+What is restated here (reference paths relative to /root/reference):
+
+* ``ranking_ref``              <- scripts/ms_marco_eval.py:189-235  (``ranking``)
+* ``generate_embeddings_ref``  <- scripts/ms_marco_eval.py:123-152
+* ``cos_sim_ref``              <- scripts/ms_marco_eval.py:155-162, src/ccrec/models/bbpr.py:485-492
+* ``lazy_score_dense_ref``     <- src/rime_lite/util/score_array.py:173-174,226-227,291-293
+                                  (MatMul(LazyDense, LazyDense.T) [+ LazySparse]).as_tensor("cpu")
+* ``assign_topk_ref``          <- src/rime_lite/util/__init__.py:117-152 (``_assign_topk``)
+* ``argsort_ref``              <- src/rime_lite/util/__init__.py:158-184 (``_argsort``)
+* ``transform_scores_ref``     <- src/ccrec/models/bbpr.py:528-545 (tile loop of ``BertBPR.transform``)
+
+The arithmetic of all of these lives in PyTorch (third-party, version unpinned by the
+reference's setup.py:10-17): ``@``/``mm``, ``F.normalize``, ``Tensor.sort``,
+``Tensor.topk``.  The restatements call the same torch ops on CPU tensors.
+
+Pinning: the reference ships NO test, golden vector or fixture for this path
+(test/ only holds test_dawid_skene.py).  The oracle is therefore pinned against
+outputs of the reference's own code executed in the build container
+(tests/golden/make_golden.py imports the unmodified reference and stores its
+outputs in tests/golden/*.npz; tests/test_oracle_golden.py replays them).
+
+``score_topk_ref`` is the arbiter for the CUDA kernels: fp32 (or fp64 when an
+additive float64 prior is present, as in the reference) scores from the
+*bf16-rounded* inputs, chunked over the corpus with a running top-k so it scales,
+ties broken by lowest id.  ``check_topk`` implements the tolerance rule of
+BASELINE.json's north_star (scores within 1e-2 relative; id sets equal except
+for swaps among items whose score lies within that tolerance of the k-th score).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import scipy.sparse as sps
+import torch
+
+MASK_NONE, MASK_SET, MASK_ADD = 0, 1, 2
+RANKING_TOPN = 1001  # scripts/ms_marco_eval.py:230
+
+
+# ----------------------------------------------------------------------------------------
+# restatements of the reference functions
+# ----------------------------------------------------------------------------------------
+def cos_sim_ref(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """scripts/ms_marco_eval.py:155-162."""
+    if a.dim() == 1:
+        a = a.unsqueeze(0)
+    if b.dim() == 1:
+        b = b.unsqueeze(0)
+    a_norm = torch.nn.functional.normalize(a, p=2, dim=1)
+    b_norm = torch.nn.functional.normalize(b, p=2, dim=1)
+    return torch.mm(a_norm, b_norm.transpose(0, 1))
+
+
+def generate_embeddings_ref(data_indices, data_dic, embedding_func, batch_size):
+    """scripts/ms_marco_eval.py:123-152 without the progress prints / torch.save."""
+    num = len(data_indices)
+    out = []
+    with torch.no_grad():
+        for step in range(math.ceil(num / batch_size)):
+            indices = data_indices[step * batch_size : (step + 1) * batch_size]
+            out.append(torch.as_tensor(embedding_func([data_dic[i] for i in indices])).to("cpu"))
+    return torch.vstack(out)
+
+
+def ranking_ref(corpus, queries, embedding_func, batch_size, block_dict=None, sim_type=None,
+                topn=RANKING_TOPN, stable=True):
+    """scripts/ms_marco_eval.py:189-235 with its four CUDA calls removed.
+
+    ``stable=True`` makes the per-row sort stable (ties -> lowest corpus position first),
+    which is one of the orders the reference's unstable ``sort`` may legally produce.
+    """
+    import pandas as pd
+
+    if sim_type is None:
+        sim_type = os.environ.get("CCREC_SIM_TYPE", "cos")
+    num_queries, num_passages = len(queries), len(corpus)
+    queries_ids, corpus_ids = list(queries.keys()), list(corpus.keys())
+    queries_embeddings = generate_embeddings_ref(queries_ids, queries, embedding_func, batch_size)
+    passage_embeddings = generate_embeddings_ref(corpus_ids, corpus, embedding_func, batch_size)
+
+    ranking_profile = {}
+    ranking_matrix = torch.zeros(num_queries, num_passages)          # :204
+    for step in range(math.ceil(num_passages / batch_size)):         # :206-218
+        pb = passage_embeddings[step * batch_size : (step + 1) * batch_size]
+        if sim_type == "cos":
+            scores = cos_sim_ref(queries_embeddings, pb)
+        else:
+            scores = queries_embeddings @ pb.T
+        ranking_matrix[:, step * batch_size : step * batch_size + pb.shape[0]] = scores
+    corpus_index = pd.Index(corpus_ids)  # hoisted out of the loop; same get_indexer result
+    for step, qid in enumerate(queries_ids):                         # :221-234
+        scores = ranking_matrix[step]
+        if block_dict is not None:
+            block_ind = corpus_index.get_indexer(block_dict[qid])
+            assert -1 not in block_ind, "block id not found"
+            scores[block_ind] = -1e6                                 # :227 assignment
+        ordered_scores, ordering = scores.sort(descending=True, stable=stable)
+        ordered_scores, ordering = ordered_scores[0:topn], ordering[0:topn]
+        ordered_pids = [corpus_ids[idx] for idx in ordering]
+        ranking_profile[qid] = dict(zip(ordered_pids, ordered_scores.numpy().tolist()))
+    return ranking_profile
+
+
+def lazy_score_dense_ref(U, V, prior=None):
+    """What ``(LazyDense(U) @ LazyDense(V).T [+ prior_csr]).as_tensor("cpu")`` evaluates to.
+
+    score_array.py:226-227 (``torch.as_tensor(self.c)``), :291-293 (``op(*children)``),
+    :173-174 (sparse -> dense).  fp32 @ fp32 -> fp32; adding a float64 CSR promotes to float64.
+    """
+    s = torch.as_tensor(np.asarray(U)) @ torch.as_tensor(np.asarray(V)).T
+    if prior is not None:
+        s = s + torch.as_tensor(sps.csr_matrix(prior).toarray())
+    return s
+
+
+def assign_topk_ref(S, k, tie_breaker=0.0, seed=None):
+    """src/rime_lite/util/__init__.py:117-152 on an already-dense matrix ``S``.
+
+    With ``tie_breaker=0`` this is ``S.topk(k).indices`` -> CSR of ones with the indices
+    in top-k order (:145-152).  Raises like torch when k > n_cols.
+    """
+    s = torch.as_tensor(np.asarray(S)) if not torch.is_tensor(S) else S
+    if tie_breaker:
+        g = torch.Generator().manual_seed(0 if seed is None else seed)
+        s = s + torch.rand(*s.shape, generator=g) * tie_breaker
+    indices = s.topk(k).indices.cpu().numpy()
+    return sps.csr_matrix(
+        (np.ones(indices.size), np.ravel(indices), np.arange(0, indices.size + 1, indices.shape[1])),
+        shape=tuple(s.shape),
+    )
+
+
+def argsort_ref(S):
+    """src/rime_lite/util/__init__.py:158-184 with tie_breaker=0: flat descending argsort."""
+    S = np.asarray(S)
+    ind = np.argsort(-S.reshape(-1), kind="stable")
+    return np.unravel_index(ind, S.shape)
+
+
+def transform_scores_ref(all_emb, i_to_ptr, j_to_ptr, batch_size, sim_type):
+    """src/ccrec/models/bbpr.py:528-545: users x items dense fp32 score matrix by item tiles."""
+    all_emb = torch.as_tensor(all_emb)
+    user_embedding = all_emb[i_to_ptr]
+    out = torch.zeros(len(i_to_ptr), len(j_to_ptr))
+    for step in range(int(np.ceil(len(j_to_ptr) / batch_size))):
+        item_ids = j_to_ptr[step * batch_size : (step + 1) * batch_size]
+        ib = all_emb[item_ids]
+        scores = cos_sim_ref(user_embedding, ib) if sim_type == "cos" else user_embedding @ ib.T
+        out[:, step * batch_size : step * batch_size + ib.shape[0]] = scores
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# the kernel arbiter
+# ----------------------------------------------------------------------------------------
+def bf16_round(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def normalize_rows_ref(x: torch.Tensor) -> torch.Tensor:
+    """F.normalize(p=2, dim=1, eps=1e-12) in fp32 (ms_marco_eval.py:160-161)."""
+    return torch.nn.functional.normalize(x.float(), p=2, dim=1)
+
+
+def canonical_mask(indptr, cols, vals, n_cols, mode):
+    """Sort columns per row and merge duplicates (sum for add, last-wins==same value for set)."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    m = sps.csr_matrix((np.asarray(vals, dtype=np.float64), np.asarray(cols, dtype=np.int64), indptr),
+                       shape=(len(indptr) - 1, n_cols))
+    if mode == MASK_SET:
+        # duplicates under assignment: keep one entry (all carry the same value in the reference)
+        coo = m.tocoo()
+        key = coo.row.astype(np.int64) * n_cols + coo.col
+        _, first = np.unique(key, return_index=True)
+        m = sps.csr_matrix((np.asarray(vals, dtype=np.float64)[first], (coo.row[first], coo.col[first])),
+                           shape=m.shape)
+    else:
+        m.sum_duplicates()
+    m.sort_indices()
+    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(np.float64)
+
+
+def score_topk_ref(Q, P, k, mask=None, mode=MASK_NONE, sim="dot", round_bf16=True, chunk=1 << 18,
+                   id_offset=0, return_f64=False):
+    """Exact top-k of ``Q @ P.T`` (+ sparse set/add mask) per row, ties -> lowest id.
+
+    Q [B,D], P [N,D] float tensors.  ``round_bf16`` rounds both to bf16 first (after the
+    fp32 L2-normalisation when ``sim == 'cos'``), matching what the device table stores.
+    ``mask`` = (indptr[B+1], cols[nnz], vals[nnz]) over the N columns.  ``mode``:
+    MASK_SET assigns ``vals`` (ranking(): -1e6, ms_marco_eval.py:227); MASK_ADD adds them in
+    float64 (rime_lite prior_score, dataset/base.py:234,279-282).
+    Returns (scores float32|float64 [B,k] descending, ids int64 [B,k] + id_offset).
+    """
+    Q = torch.as_tensor(Q).float()
+    P = torch.as_tensor(P).float()
+    B, N = Q.shape[0], P.shape[0]
+    if k > N:
+        raise RuntimeError("selected index k out of range")
+    if sim == "cos":
+        Q, P = normalize_rows_ref(Q), normalize_rows_ref(P)
+    if round_bf16:
+        Q, P = bf16_round(Q), bf16_round(P)
+    use64 = mode == MASK_ADD
+    dt = torch.float64 if use64 else torch.float32
+    best_s = torch.full((B, 0), 0, dtype=dt)
+    best_i = torch.zeros((B, 0), dtype=torch.int64)
+    if mask is not None and mode != MASK_NONE:
+        indptr, cols, vals = canonical_mask(mask[0], mask[1], mask[2], N, mode)
+        mcsr = sps.csr_matrix((vals, cols, indptr), shape=(B, N))
+    else:
+        mcsr = None
+    old = torch.backends.cuda.matmul.allow_tf32
+    for s0 in range(0, N, chunk):
+        s1 = min(N, s0 + chunk)
+        sc = (Q @ P[s0:s1].T).to(dt)
+        if mcsr is not None:
+            sub = mcsr[:, s0:s1].tocoo()
+            r = torch.as_tensor(sub.row, dtype=torch.int64)
+            c = torch.as_tensor(sub.col, dtype=torch.int64)
+            v = torch.as_tensor(sub.data, dtype=dt)
+            if mode == MASK_SET:
+                sc[r, c] = v
+            else:
+                sc[r, c] = sc[r, c] + v
+        ids = torch.arange(s0, s1, dtype=torch.int64).expand(B, -1)
+        cat_s = torch.cat([best_s, sc], dim=1)
+        cat_i = torch.cat([best_i, ids], dim=1)
+        # stable descending sort == ties -> earlier position == lower id (best_* precede and
+        # hold lower ids than the current chunk)
+        kk = min(k, cat_s.shape[1])
+        o = torch.sort(cat_s, dim=1, descending=True, stable=True)
+        best_s = o.values[:, :kk].contiguous()
+        best_i = torch.gather(cat_i, 1, o.indices[:, :kk]).contiguous()
+    torch.backends.cuda.matmul.allow_tf32 = old
+    out_s = best_s if (return_f64 or not use64) else best_s
+    if not return_f64:
+        out_s = out_s.to(torch.float32)
+    return out_s, best_i + id_offset
+
+
+def full_scores_ref(Q, P, mask=None, mode=MASK_NONE, sim="dot", round_bf16=True):
+    """Dense [B,N] score matrix under the same conventions as ``score_topk_ref`` (small cases)."""
+    Q = torch.as_tensor(Q).float()
+    P = torch.as_tensor(P).float()
+    if sim == "cos":
+        Q, P = normalize_rows_ref(Q), normalize_rows_ref(P)
+    if round_bf16:
+        Q, P = bf16_round(Q), bf16_round(P)
+    s = Q @ P.T
+    if mask is not None and mode != MASK_NONE:
+        indptr, cols, vals = canonical_mask(mask[0], mask[1], mask[2], P.shape[0], mode)
+        m = sps.csr_matrix((vals, cols, indptr), shape=s.shape).tocoo()
+        r, c = torch.as_tensor(m.row, dtype=torch.int64), torch.as_tensor(m.col, dtype=torch.int64)
+        if mode == MASK_SET:
+            s[r, c] = torch.as_tensor(m.data, dtype=torch.float32)
+        else:
+            s = s.double()
+            s[r, c] += torch.as_tensor(m.data, dtype=torch.float64)
+    return s
+
+
+def check_topk(got_scores, got_ids, full_scores=None, ref_scores=None, ref_ids=None, rtol=1e-2,
+               atol=1e-6, ordered_slack=True):
+    """The north_star tolerance rule.  Returns a list of human-readable violations (empty == ok).
+
+    Either ``full_scores`` [B,N] (small cases: every returned id is checked against its true
+    score) or ``ref_scores``/``ref_ids`` [B,k] from ``score_topk_ref`` must be given.
+
+    * scores: |s - s_ref| <= rtol*|s_ref| + atol for the score of every returned id
+      (vs the full matrix) or rank-wise (vs the reference list);
+    * ids: distinct; set-equal to the reference except for items whose reference score lies
+      within the tolerance of the reference k-th score;
+    * order: returned scores non-increasing.
+    """
+    errs = []
+    gs = np.asarray(got_scores, dtype=np.float64)
+    gi = np.asarray(got_ids, dtype=np.int64)
+    B, k = gi.shape
+    for b in range(B):
+        if len(set(gi[b].tolist())) != k:
+            errs.append(f"row {b}: duplicate ids")
+            continue
+        if np.any(np.diff(gs[b]) > 0):
+            errs.append(f"row {b}: scores not descending")
+        if full_scores is not None:
+            row = np.asarray(full_scores[b], dtype=np.float64)
+            true = row[gi[b]]
+            bad = np.abs(gs[b] - true) > rtol * np.abs(true) + atol
+            if bad.any():
+                j = int(np.argmax(bad))
+                errs.append(f"row {b}: score of id {gi[b, j]} is {gs[b, j]} vs {true[j]}")
+            kth = np.sort(row)[::-1][k - 1]
+            tol = rtol * abs(kth) + atol
+            # every returned id must be >= kth - tol ; every item > kth + tol must be returned
+            if (true < kth - tol).any():
+                j = int(np.argmin(true))
+                errs.append(f"row {b}: id {gi[b, j]} (score {true[j]}) below k-th {kth}")
+            must = np.nonzero(row > kth + tol)[0]
+            missing = np.setdiff1d(must, gi[b])
+            if missing.size:
+                errs.append(f"row {b}: missing ids {missing[:5].tolist()} above k-th {kth}")
+        else:
+            rs = np.asarray(ref_scores[b], dtype=np.float64)
+            ri = np.asarray(ref_ids[b], dtype=np.int64)
+            bad = np.abs(gs[b] - rs) > rtol * np.abs(rs) + atol
+            if bad.any():
+                j = int(np.argmax(bad))
+                errs.append(f"row {b}: rank {j} score {gs[b, j]} vs ref {rs[j]}")
+            kth = rs[-1]
+            tol = rtol * abs(kth) + atol
+            sure = ri[rs > kth + tol]
+            missing = np.setdiff1d(sure, gi[b])
+            if missing.size:
+                errs.append(f"row {b}: missing ids {missing[:5].tolist()}")
+            extra = np.setdiff1d(gi[b], ri)
+            if extra.size:
+                # extras are only allowed as near-tie swaps: their returned score must be near kth
+                pos = np.nonzero(np.isin(gi[b], extra))[0]
+                if (gs[b][pos] < kth - tol).any():
+                    errs.append(f"row {b}: extra ids {extra[:5].tolist()} below k-th {kth}")
+        if len(errs) > 20:
+            break
+    return errs

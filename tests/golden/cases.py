@@ -1,0 +1,102 @@
+"""Seeded synthetic inputs shared by make_golden.py (which runs the real reference on
+them) and by the tests (which replay them through the oracle and the CUDA path).
+
+``np.random.RandomState`` (legacy MT19937 stream) is frozen by numpy's compatibility
+policy, so regenerating from the seed reproduces the exact inputs the goldens were made
+from; the goldens only store the reference's OUTPUTS.
+"""
+import numpy as np
+import scipy.sparse as sps
+
+
+def embeddings(seed, n, d, clustered=False):
+    rs = np.random.RandomState(seed)
+    if not clustered:
+        return rs.standard_normal((n, d)).astype(np.float32)
+    centres = rs.standard_normal((max(4, n // 16), d)).astype(np.float32)
+    x = centres[rs.randint(0, len(centres), size=n)] + 0.5 * rs.standard_normal((n, d)).astype(np.float32)
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+class TextTable:
+    """A synthetic ``embedding_func``: text key -> fixed embedding row."""
+
+    def __init__(self, table):
+        import torch
+
+        self.table = torch.as_tensor(table)
+        self.calls = 0
+
+    def __call__(self, texts):
+        import torch
+
+        self.calls += 1
+        idx = torch.as_tensor([int(t.split("#")[1]) for t in texts], dtype=torch.int64)
+        return self.table[idx]
+
+
+def ranking_case(name):
+    """-> dict(corpus, queries, table, batch_size, block_dict, sim_type)."""
+    spec = RANKING_CASES[name]
+    n, q, d = spec["n"], spec["q"], spec["d"]
+    same = spec.get("queries_are_corpus", False)
+    emb = embeddings(spec["seed"], n if same else n + q, d, spec.get("clustered", False))
+    corpus = {f"p{i}": f"text#{i}" for i in range(n)}
+    if same:
+        queries = {f"p{i}": f"text#{i}" for i in range(q)}
+    else:
+        queries = {f"q{i}": f"text#{n + i}" for i in range(q)}
+    block_dict = None
+    if spec.get("brands"):
+        rs = np.random.RandomState(spec["seed"] + 1)
+        brand = rs.zipf(1.1, size=n) % spec["brands"]
+        groups = {}
+        for i, b in enumerate(brand):
+            groups.setdefault(int(b), []).append(f"p{i}")
+        if same:
+            block_dict = {f"p{i}": groups[int(brand[i])] for i in range(q)}
+        else:
+            block_dict = {f"q{i}": groups[int(brand[rs.randint(n)])] for i in range(q)}
+    return dict(corpus=corpus, queries=queries, table=emb, batch_size=spec["batch_size"],
+                block_dict=block_dict, sim_type=spec["sim"])
+
+
+RANKING_CASES = {
+    # name: N passages, Q queries, dim, similarity, encoder/tile batch, optional brand blocks
+    "dot_n1500": dict(seed=11, n=1500, q=12, d=64, sim="dot", batch_size=512),
+    "dot_d768_n300": dict(seed=12, n=300, q=8, d=768, sim="dot", batch_size=128),
+    "cos_block_n1300": dict(seed=13, n=1300, q=16, d=64, sim="cos", batch_size=512, brands=40,
+                            queries_are_corpus=True, clustered=True),
+    # heavy blocking: fewer than 1001 unmasked items for some rows -> -1e6 entries are returned
+    "dot_block_tail_n1100": dict(seed=14, n=1100, q=10, d=64, sim="dot", batch_size=256, brands=5,
+                                 queries_are_corpus=True),
+}
+
+
+def rime_case(name):
+    """-> dict(U [B,d] f32, V [N,d] f32, prior csr float64 [B,N] or None, k)."""
+    spec = RIME_CASES[name]
+    b, n, d = spec["b"], spec["n"], spec["d"]
+    U = embeddings(spec["seed"], b, d)
+    V = embeddings(spec["seed"] + 100, n, d)
+    prior = None
+    if spec.get("prior"):
+        rs = np.random.RandomState(spec["seed"] + 200)
+        rows, cols, vals = [], [], []
+        for r in range(b):
+            # seen history: -1e10 (dataset/base.py:234); reranking candidates: +prior (:279-282)
+            seen = rs.choice(n, size=rs.randint(0, 4), replace=False)
+            cand = rs.choice(n, size=rs.randint(1, 6), replace=False)
+            for c in seen:
+                rows.append(r), cols.append(int(c)), vals.append(-1e10)
+            for c in cand:
+                rows.append(r), cols.append(int(c)), vals.append(float(spec["prior"]))
+        prior = sps.csr_matrix((np.array(vals), (np.array(rows), np.array(cols))), shape=(b, n))
+    return dict(U=U, V=V, prior=prior, k=spec["k"])
+
+
+RIME_CASES = {
+    "plain_k5": dict(seed=21, b=9, n=400, d=32, k=5),
+    "mask_prior_k1": dict(seed=22, b=40, n=700, d=48, k=1, prior=1e5),
+    "mask_prior_k10": dict(seed=23, b=17, n=257, d=64, k=10, prior=1.0),
+}

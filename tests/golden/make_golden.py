@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference code in this container.
+
+    python tests/golden/make_golden.py
+
+Needs /root/reference (absent on the GPU box -> the committed .npz files are what travels).
+Each golden stores only the reference's outputs; inputs are regenerated from seeds by
+tests/golden/cases.py.
+
+* ranking_<case>.npz : output of scripts/ms_marco_eval.py::ranking (real function, with
+  Tensor.cuda()/torch.cuda.synchronize patched to no-ops because this box has no GPU):
+  per query the ordered corpus positions and float scores (<=1001 entries).
+* rime_<case>.npz    : outputs of the real rime_lite code: ``_assign_topk`` CSR indices,
+  the dense ``as_tensor`` matrix dtype, ``_argsort`` head, ``evaluate_item_rec`` metrics.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import cases  # noqa: E402
+import _ref_loader  # noqa: E402
+
+
+def make_ranking():
+    me = _ref_loader.load_ms_marco_eval()
+    for name in cases.RANKING_CASES:
+        c = cases.ranking_case(name)
+        os.environ["CCREC_SIM_TYPE"] = c["sim_type"]
+        with _ref_loader.cpu_as_cuda():
+            prof = me.ranking(c["corpus"], c["queries"], cases.TextTable(c["table"]), c["batch_size"],
+                              c["block_dict"])
+        qids = list(c["queries"].keys())
+        pos = {pid: i for i, pid in enumerate(c["corpus"].keys())}
+        order = np.array([[pos[p] for p in prof[q].keys()] for q in qids], dtype=np.int32)
+        scores = np.array([list(prof[q].values()) for q in qids], dtype=np.float64)
+        np.savez_compressed(os.path.join(HERE, f"ranking_{name}.npz"), order=order, scores=scores)
+        print("ranking", name, order.shape)
+
+
+def make_rime():
+    ru = _ref_loader.load_rime_lite_util()
+    rm = _ref_loader.load_rime_lite_metrics()
+    for name in cases.RIME_CASES:
+        c = cases.rime_case(name)
+        S = ru.LazyDenseMatrix(c["U"]) @ ru.LazyDenseMatrix(c["V"]).T
+        if c["prior"] is not None:
+            S = S + c["prior"]
+        dense = S.as_tensor("cpu")
+        torch.manual_seed(0)
+        csr = ru._assign_topk(S, c["k"], device="cpu")
+        idx_topk_order = csr.indices.reshape(len(c["U"]), c["k"]).astype(np.int32).copy()
+        # batch_size=4 exercises the row-slicing / collate contract (util/__init__.py:126-131)
+        torch.manual_seed(0)
+        csr_b = ru._assign_topk(S, c["k"], device="cpu", batch_size=4)
+        idx_b_topk_order = csr_b.indices.reshape(len(c["U"]), c["k"]).astype(np.int32).copy()
+        ar, ac = ru._argsort(S, tie_breaker=0, device="cpu")
+        target = (csr_b > 0).astype(np.float64)  # any 0/1 target works for the metric replay
+        torch.manual_seed(0)
+        metrics = rm.evaluate_item_rec(target, S, c["k"])
+        np.savez_compressed(
+            os.path.join(HERE, f"rime_{name}.npz"),
+            indices=idx_topk_order,  # copied before scipy comparisons sort them in place
+            indices_batched=idx_b_topk_order,
+            indptr=csr.indptr.astype(np.int64),
+            data=csr.data,
+            shape=np.array(csr.shape),
+            dense_dtype=str(dense.dtype),
+            dense_head=dense[:4, :16].numpy().astype(np.float64),
+            argsort_rows=ar[:64].astype(np.int32),
+            argsort_cols=ac[:64].astype(np.int32),
+            metric_names=np.array(sorted(metrics)),
+            metric_values=np.array([metrics[m] for m in sorted(metrics)], dtype=np.float64),
+        )
+        print("rime", name, csr.shape, dense.dtype, metrics)
+
+
+if __name__ == "__main__":
+    assert _ref_loader.reference_available(), "needs /root/reference"
+    make_ranking()
+    make_rime()
