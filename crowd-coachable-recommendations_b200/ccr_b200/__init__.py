@@ -1,0 +1,36 @@
+"""ccr_b200 -- B200-native candidate score-and-rank for Crowd Coachable Recommendations.
+
+Public surface (mirrors the reference's call sites for this path):
+
+* ``ranking`` / ``generate_embeddings`` / ``cos_sim``      <- scripts/ms_marco_eval.py
+* ``_assign_topk`` / ``assign_topk``                       <- src/rime_lite/util/__init__.py
+* ``LazyDenseMatrix`` ... ``auto_cast_lazy_score``         <- src/rime_lite/util/score_array.py
+* ``evaluate_item_rec`` / ``evaluate_assigned``            <- src/rime_lite/metrics/__init__.py
+* ``EmbeddingTable`` / ``ShardedIndex``                    (residency + row-sharding layer)
+* ``score_topk`` / ``merge_topk``                          (thin wrappers of the C ABI)
+"""
+from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, MASK_ADD, MASK_NONE, MASK_SET, LIB_PATH  # noqa: F401
+from .engine import SparseMask, ingest_rows, merge_topk, score_dense, score_topk  # noqa: F401
+from .table import EmbeddingTable  # noqa: F401
+from .score_array import (  # noqa: F401
+    ElementWiseExpression,
+    LazyDenseMatrix,
+    LazyScoreBase,
+    LazySparseMatrix,
+    MatMulExpression,
+    auto_cast_lazy_score,
+    fused_plan,
+    get_batch_size,
+    score_op,
+)
+from .util import _assign_topk, assign_topk, topk_lazy  # noqa: F401
+from .metrics import evaluate_assigned, evaluate_item_rec  # noqa: F401
+from .ranking import (  # noqa: F401
+    build_block_mask,
+    cos_sim,
+    generate_embeddings,
+    generate_embeddings_device,
+    ranking,
+    ranking_tensors,
+)
+from .dist import ShardedIndex, shard_bounds  # noqa: F401

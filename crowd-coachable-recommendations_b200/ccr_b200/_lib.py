@@ -1,0 +1,94 @@
+"""ctypes binding of libccr_b200.so (C ABI: include/ccr_b200.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or a CUDA device is
+not present when a kernel is requested, this raises instead of computing something else.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libccr_b200.so")
+
+MASK_NONE, MASK_SET, MASK_ADD = 0, 1, 2
+ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
+FLAG_ALLOW_SHORT = 0x10
+MAX_K = 2048
+
+OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, EK_RANGE = 0, -1, -2, -3, -4, -5
+
+# every symbol include/ccr_b200.h declares (tests check they are all exported)
+EXPORTS = [
+    "ccr_abi_version",
+    "ccr_last_error_string",
+    "ccr_score_topk_bf16",
+    "ccr_score_topk_workspace_bytes",
+    "ccr_merge_topk",
+    "ccr_ingest_rows_f32",
+    "ccr_normalize_rows_bf16",
+    "ccr_score_dense_f32",
+    "ccr_choose_algo",
+    "ccr_plan_info",
+]
+
+_lib = None
+
+
+class CcrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libccr_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise if the CUDA extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C crowd-coachable-recommendations_b200/csrc`."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    c = ctypes
+    vp, i64, i32, sz = c.c_void_p, c.c_int64, c.c_int, c.c_size_t
+    L.ccr_abi_version.restype = i32
+    L.ccr_last_error_string.restype = c.c_char_p
+    L.ccr_score_topk_bf16.restype = i32
+    L.ccr_score_topk_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, vp, vp, i64, i32, i64,
+                                      vp, vp, vp, vp, sz, i32, vp]
+    L.ccr_score_topk_workspace_bytes.restype = sz
+    L.ccr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32, i64, i32]
+    L.ccr_merge_topk.restype = i32
+    L.ccr_merge_topk.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
+    L.ccr_ingest_rows_f32.restype = i32
+    L.ccr_ingest_rows_f32.argtypes = [vp, i64, i32, i64, vp, i64, i32, vp]
+    L.ccr_normalize_rows_bf16.restype = i32
+    L.ccr_normalize_rows_bf16.argtypes = [vp, i64, i32, i64, vp, i64, vp]
+    L.ccr_score_dense_f32.restype = i32
+    L.ccr_score_dense_f32.argtypes = [vp, i64, i64, vp, i64, i64, i32, vp, i64, vp]
+    L.ccr_choose_algo.restype = i32
+    L.ccr_choose_algo.argtypes = [i64, i64, i32, i32]
+    L.ccr_plan_info.restype = i32
+    L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i32, c.POINTER(c.c_int32)]
+    if L.ccr_abi_version() != 1:
+        raise RuntimeError("libccr_b200 ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != OK:
+        msg = lib().ccr_last_error_string().decode("utf-8", "replace")
+        if rc == EK_RANGE:
+            raise RuntimeError(msg)  # torch.topk raises RuntimeError("selected index k out of range")
+        if rc in (EINVAL, EUNSUPPORTED):
+            raise ValueError(f"libccr_b200: {msg}")
+        raise CcrError(rc, msg)
+
+
+def plan_info(B, n_items, D, k, flags=0):
+    arr = (ctypes.c_int32 * 4)()
+    check(lib().ccr_plan_info(B, n_items, D, k, flags, arr))
+    return {"n_q_tiles": arr[0], "n_splits": arr[1], "cand_capacity": arr[2], "algo": arr[3]}

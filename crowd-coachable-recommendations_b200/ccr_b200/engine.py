@@ -1,0 +1,224 @@
+"""Host side of the fused score + mask + top-k call: tensors -> raw pointers -> C ABI.
+
+PyTorch is used for device memory, streams and (in dist.py) torch.distributed only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MASK_ADD, MASK_NONE, MASK_SET  # noqa: F401
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device (ccr_b200 has no CPU path)")
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _Workspace:
+    """Per-device scratch that only grows; owned by the caller side of the ABI."""
+
+    def __init__(self):
+        self._buf = {}
+
+    def get(self, device, nbytes):
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        b = self._buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = None
+            self._buf[key] = None
+            b = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            self._buf[key] = b
+        return b
+
+    def clear(self):
+        self._buf.clear()
+
+
+workspace = _Workspace()
+
+
+class SparseMask:
+    """Device CSR over item columns: the history / block mask and additive priors.
+
+    ``mode`` MASK_SET: value assigned (ranking(): -1e6, scripts/ms_marco_eval.py:227);
+    MASK_ADD: value added in float64 (rime_lite prior_score, src/rime_lite/dataset/base.py:234,279-282).
+    Columns are sorted and unique per row (duplicates: summed for ADD, collapsed for SET).
+    """
+
+    def __init__(self, indptr, cols, vals, n_cols, mode, device):
+        self.n_rows = len(indptr) - 1
+        self.n_cols = int(n_cols)
+        self.mode = mode
+        self.nnz = int(indptr[-1])
+        self.host = (np.asarray(indptr, dtype=np.int64), np.asarray(cols, dtype=np.int32),
+                     np.asarray(vals, dtype=np.float64))
+        self.device = torch.device(device)
+        self.indptr = torch.as_tensor(self.host[0]).to(self.device)
+        self.cols = torch.as_tensor(self.host[1]).to(self.device)
+        self.vals = torch.as_tensor(self.host[2]).to(self.device)
+
+    @classmethod
+    def from_scipy(cls, csr, mode, device):
+        import scipy.sparse as sps
+
+        m = sps.csr_matrix(csr, dtype=np.float64, copy=True)
+        if mode == MASK_SET:
+            m.data[:] = np.where(m.data == 0, 0.0, m.data)
+            # collapse duplicates without summing: keep first
+            coo = m.tocoo()
+            key = coo.row.astype(np.int64) * m.shape[1] + coo.col
+            _, first = np.unique(key, return_index=True)
+            m = sps.csr_matrix((coo.data[first], (coo.row[first], coo.col[first])), shape=m.shape)
+        else:
+            m.sum_duplicates()
+        m.sort_indices()
+        return cls(m.indptr, m.indices, m.data, m.shape[1], mode, device)
+
+    @classmethod
+    def from_lists(cls, rows_of_cols, n_cols, value, mode, device):
+        """rows_of_cols: iterable of per-row iterables of column positions (duplicates allowed)."""
+        indptr, cols = [0], []
+        for r in rows_of_cols:
+            u = np.unique(np.asarray(list(r), dtype=np.int64))
+            if u.size and (u[0] < 0 or u[-1] >= n_cols):
+                raise IndexError("mask column out of range")
+            cols.append(u)
+            indptr.append(indptr[-1] + u.size)
+        cols = np.concatenate(cols) if cols else np.zeros(0, dtype=np.int64)
+        vals = np.full(cols.shape, float(value))
+        return cls(indptr, cols, vals, n_cols, mode, device)
+
+    def rows(self, start, stop):
+        ip, c, v = self.host
+        a, b = ip[start], ip[stop]
+        return SparseMask(ip[start : stop + 1] - a, c[a:b], v[a:b], self.n_cols, self.mode, self.device)
+
+    def column_shard(self, lo, hi):
+        """Entries with lo <= col < hi, re-based to local column ids (row-sharded tables)."""
+        ip, c, v = self.host
+        keep = (c >= lo) & (c < hi)
+        row_of = np.repeat(np.arange(self.n_rows), np.diff(ip))
+        counts = np.bincount(row_of[keep], minlength=self.n_rows)
+        new_ip = np.concatenate([[0], np.cumsum(counts)])
+        return SparseMask(new_ip, c[keep] - lo, v[keep], hi - lo, self.mode, self.device)
+
+
+def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_lib.ALGO_AUTO,
+               allow_short=False, want_f64=False, n_items=None, D=None):
+    """Fused ``topk(q @ items.T [mask], k)`` on the device (C ABI: ccr_score_topk_bf16).
+
+    q [B, ldq] bf16 cuda, items [N, ldi] bf16 cuda (row-major, last dim contiguous).
+    Returns (scores float32 [B,k] descending, ids int64 [B,k]) and, with ``want_f64``, the
+    float64 values the order was decided on.
+    """
+    _require_cuda(q, "q")
+    _require_cuda(items, "items")
+    if q.dtype != torch.bfloat16 or items.dtype != torch.bfloat16:
+        raise TypeError("q and items must be bfloat16 (use EmbeddingTable / ingest_rows to convert)")
+    if q.dim() != 2 or items.dim() != 2 or q.stride(1) != 1 or items.stride(1) != 1:
+        raise ValueError("q and items must be 2-d with a contiguous last dimension")
+    dev = q.device
+    B = q.shape[0]
+    N = items.shape[0] if n_items is None else int(n_items)
+    D = q.shape[1] if D is None else int(D)
+    ldq = q.stride(0) if B > 1 else max(q.stride(0), q.shape[1])
+    ldi = items.stride(0) if items.shape[0] > 1 else max(items.stride(0), items.shape[1])
+    k = int(k)
+    flags = int(algo) | (_lib.FLAG_ALLOW_SHORT if allow_short else 0)
+    L = _lib.lib()
+    if mask is not None:
+        if mask.n_rows != B:
+            raise ValueError(f"mask has {mask.n_rows} rows, queries {B}")
+        if mask.n_cols != N:
+            raise ValueError(f"mask has {mask.n_cols} columns, table shard {N}")
+    nnz = mask.nnz if mask is not None else 0
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    out_d = torch.empty((B, k), dtype=torch.float64, device=dev) if want_f64 else None
+    with torch.cuda.device(dev):
+        need = L.ccr_score_topk_workspace_bytes(B, N, D, k, nnz, flags)
+        if need == 0 and B > 0:
+            # invalid shape: let the real call produce the error message
+            need = 256
+        ws = workspace.get(dev, need)
+        rc = L.ccr_score_topk_bf16(
+            q.data_ptr(), B, ldq, items.data_ptr() if N > 0 else None, N, ldi, D, k,
+            mask.indptr.data_ptr() if mask is not None else None,
+            mask.cols.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
+            mask.vals.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
+            nnz, mask.mode if mask is not None else MASK_NONE, int(id_offset),
+            out_s.data_ptr(), out_d.data_ptr() if want_f64 else None, out_i.data_ptr(),
+            ws.data_ptr(), ws.numel(), flags, _stream_ptr(dev))
+    _lib.check(rc)
+    return (out_s, out_i, out_d) if want_f64 else (out_s, out_i)
+
+
+def merge_topk(scores64, ids, k_out):
+    """[G,B,k_in] float64 / int64 sorted runs -> merged top-k_out (C ABI: ccr_merge_topk)."""
+    _require_cuda(scores64, "scores64")
+    G, B, k_in = scores64.shape
+    scores64 = scores64.contiguous()
+    ids = ids.contiguous()
+    dev = scores64.device
+    out_s = torch.empty((B, k_out), dtype=torch.float32, device=dev)
+    out_d = torch.empty((B, k_out), dtype=torch.float64, device=dev)
+    out_i = torch.empty((B, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ccr_merge_topk(scores64.data_ptr(), ids.data_ptr(), G, B, k_in, k_out, out_s.data_ptr(),
+                                       out_d.data_ptr(), out_i.data_ptr(), _stream_ptr(dev))
+    _lib.check(rc)
+    return out_s, out_i, out_d
+
+
+def ingest_rows(src, dst, normalize=False):
+    """fp32 (or bf16) rows on the device -> bf16 table rows, optional fp32 L2 normalisation."""
+    _require_cuda(src, "src")
+    _require_cuda(dst, "dst")
+    if dst.dtype != torch.bfloat16 or dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ValueError("dst must be bf16 and both must have a contiguous last dimension")
+    n, D = src.shape
+    if dst.shape[0] != n or dst.shape[1] < D:
+        raise ValueError("dst shape mismatch")
+    ld_src = src.stride(0) if n > 1 else max(src.stride(0), D)
+    ld_dst = dst.stride(0) if n > 1 else max(dst.stride(0), dst.shape[1])
+    L = _lib.lib()
+    with torch.cuda.device(src.device):
+        if src.dtype == torch.float32:
+            rc = L.ccr_ingest_rows_f32(src.data_ptr(), n, D, ld_src, dst.data_ptr(), ld_dst, int(bool(normalize)),
+                                       _stream_ptr(src.device))
+        elif src.dtype == torch.bfloat16:
+            if not normalize:
+                dst[:, :D].copy_(src)
+                if dst.shape[1] > D:
+                    dst[:, D:].zero_()
+                return dst
+            rc = L.ccr_normalize_rows_bf16(src.data_ptr(), n, D, ld_src, dst.data_ptr(), ld_dst,
+                                           _stream_ptr(src.device))
+        else:
+            raise TypeError(f"unsupported source dtype {src.dtype}")
+    _lib.check(rc)
+    return dst
+
+
+def score_dense(q, items, n_items=None, D=None):
+    """Dense fp32 [B, N] scores (small reranking sets / LazyScore.as_tensor)."""
+    _require_cuda(q, "q")
+    B = q.shape[0]
+    N = items.shape[0] if n_items is None else n_items
+    D = q.shape[1] if D is None else D
+    out = torch.empty((B, N), dtype=torch.float32, device=q.device)
+    if B == 0 or N == 0:
+        return out
+    ldq = q.stride(0) if B > 1 else max(q.stride(0), q.shape[1])
+    ldi = items.stride(0) if items.shape[0] > 1 else max(items.stride(0), items.shape[1])
+    with torch.cuda.device(q.device):
+        rc = _lib.lib().ccr_score_dense_f32(q.data_ptr(), B, ldq, items.data_ptr(), N, ldi, D, out.data_ptr(), N,
+                                            _stream_ptr(q.device))
+    _lib.check(rc)
+    return out

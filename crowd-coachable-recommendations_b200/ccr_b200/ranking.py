@@ -1,0 +1,122 @@
+"""Drop-in for the reference's dense retrieval entry point.
+
+``ranking(corpus, queries, embedding_func, batch_size, block_dict=None)`` keeps the signature,
+inputs and return value of scripts/ms_marco_eval.py:189-235 -- ``{qid: {pid: score}}`` holding
+the best 1001 (or N) passages per query in descending score order, block-listed passages
+carrying -1e6 -- but never builds the Q x N host matrix nor sorts full rows: embeddings go
+straight into a device-resident bf16 table and one fused kernel does score + mask + top-k.
+
+Deliberate deviations (documented in DESIGN.md): scores come from bf16-rounded embeddings with
+fp32 accumulation (the reference's GPU path under autocast is fp16-in/fp16-out,
+scripts/al_0_rank.py:125); exact ties are ordered by corpus position (reference: unspecified).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import engine
+from .table import EmbeddingTable
+
+RANKING_TOPN = 1001  # scripts/ms_marco_eval.py:230
+BLOCK_VALUE = -1e6   # scripts/ms_marco_eval.py:227
+QUERY_CHUNK = 8192   # query rows per fused call (bounds workspace and the [B,k] result)
+
+
+def cos_sim(a: torch.Tensor, b: torch.Tensor):
+    """scripts/ms_marco_eval.py:155-162 on the device path: fp32 normalise -> bf16 -> dense scores."""
+    a = torch.as_tensor(a)
+    b = torch.as_tensor(b)
+    if a.dim() == 1:
+        a = a.unsqueeze(0)
+    if b.dim() == 1:
+        b = b.unsqueeze(0)
+    t = EmbeddingTable.from_tensor(b, normalize=True)
+    return t.dense_scores(a)
+
+
+def generate_embeddings(data_indices, data_dic, embedding_func, batch_size, embedding_size=768, name=None):
+    """Reference-compatible signature (scripts/ms_marco_eval.py:123-152): returns a CPU fp32
+    tensor.  Kept for callers that want the host copy; ``ranking`` uses
+    ``generate_embeddings_device`` instead."""
+    out = []
+    with torch.no_grad():
+        for step in range(math.ceil(len(data_indices) / batch_size)):
+            idx = data_indices[step * batch_size : (step + 1) * batch_size]
+            out.append(torch.as_tensor(embedding_func([data_dic[i] for i in idx])).to("cpu"))
+    emb = torch.vstack(out) if out else torch.zeros(0, embedding_size)
+    if name is not None:
+        torch.save(emb, name)
+    return emb
+
+
+def generate_embeddings_device(data_indices, data_dic, embedding_func, batch_size, normalize=False,
+                               device="cuda", id_offset=0, name=None):
+    """Encoder batches -> device bf16 table without the host round trip."""
+    table = None
+    with torch.no_grad():
+        for step in range(math.ceil(len(data_indices) / batch_size)):
+            idx = data_indices[step * batch_size : (step + 1) * batch_size]
+            emb = torch.as_tensor(embedding_func([data_dic[i] for i in idx]))
+            if table is None:
+                table = EmbeddingTable(len(data_indices), emb.shape[1], device=device, normalize=normalize,
+                                       id_offset=id_offset)
+            table.append(emb)
+    if table is None:
+        table = EmbeddingTable(0, 768, device=device, normalize=normalize, id_offset=id_offset)
+    if name is not None:
+        table.save(name)
+    return table
+
+
+def build_block_mask(queries_ids, corpus_ids, block_dict, device):
+    """block_dict {qid: [pid, ...]} -> SparseMask(set -1e6).  Mirrors ms_marco_eval.py:225-227
+    including the "block id not found" assertion, with the pid->position index built once
+    instead of once per query."""
+    import pandas as pd
+
+    index = pd.Index(corpus_ids)
+    rows = []
+    for qid in queries_ids:
+        ind = index.get_indexer(block_dict[qid])
+        assert -1 not in ind, "block id not found"
+        rows.append(ind)
+    return engine.SparseMask.from_lists(rows, len(corpus_ids), BLOCK_VALUE, engine.MASK_SET, device)
+
+
+def ranking_tensors(query_table, passage_table, k, mask=None, algo=0):
+    """Core of ``ranking``: resident tables -> (scores [Q,k] f32, positions [Q,k] i64) on the host."""
+    Q = len(query_table)
+    scores = np.empty((Q, k), dtype=np.float32)
+    order = np.empty((Q, k), dtype=np.int64)
+    for s in range(0, Q, QUERY_CHUNK):
+        e = min(Q, s + QUERY_CHUNK)
+        m = mask.rows(s, e) if mask is not None else None
+        sc, ids = passage_table.search(query_table.data[s:e], k, mask=m, algo=algo, encoded=True)
+        scores[s:e] = sc.cpu().numpy()
+        order[s:e] = ids.cpu().numpy()
+    return scores, order
+
+
+def ranking(corpus, queries, embedding_func, batch_size, block_dict=None, device="cuda", algo=0):
+    sim = os.environ["CCREC_SIM_TYPE"]  # KeyError when unset, like ms_marco_eval.py:212
+    normalize = sim == "cos"
+    queries_ids, corpus_ids = list(queries.keys()), list(corpus.keys())
+    q_table = generate_embeddings_device(queries_ids, queries, embedding_func, batch_size, normalize, device)
+    p_table = generate_embeddings_device(corpus_ids, corpus, embedding_func, batch_size, normalize, device)
+    if len(queries_ids) == 0:
+        return {}
+    mask = None
+    if block_dict is not None:
+        print("using block_dict")
+        mask = build_block_mask(queries_ids, corpus_ids, block_dict, p_table.device)
+    k = min(RANKING_TOPN, len(corpus_ids))
+    scores, order = ranking_tensors(q_table, p_table, k, mask, algo=algo)
+    corpus_arr = np.asarray(corpus_ids, dtype=object)
+    ranking_profile = {}
+    for step, qid in enumerate(queries_ids):
+        ranking_profile[qid] = dict(zip(corpus_arr[order[step]].tolist(), scores[step].tolist()))
+    return ranking_profile

@@ -1,0 +1,264 @@
+// C ABI (include/ccr_b200.h): argument validation, launch planning, workspace carving.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ccr_b200.h"
+#include "ccr_params.cuh"
+
+using namespace ccr;
+
+static thread_local char g_err[512] = "";
+static void* g_status_override = nullptr;  // diagnostics: host-mapped DeviceStatus (tests only)
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int device_sm_count() {
+  static int cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return 148; }
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = 148;
+    }
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+namespace {
+struct Plan {
+  int algo;
+  int n_q_tiles;  // TC: query tiles of 128; SIMT: groups of 8
+  int rows_pad;
+  int S;
+  int C;
+  size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, total;
+};
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int splits_tc(int nq, long long tiles, int sms) {
+  long long smax = tiles < 1 ? 1 : tiles;
+  long long s0 = (sms + nq - 1) / nq;
+  if (s0 < 1) s0 = 1;
+  if (s0 >= smax) return (int)smax;
+  long long best = s0;
+  double best_waste = 2.0;
+  long long send = s0 * 4 + 40;
+  if (send > smax) send = smax;
+  for (long long s = s0; s <= send; ++s) {
+    long long units = (long long)nq * s;
+    long long waves = (units + sms - 1) / sms;
+    double waste = (double)(waves * sms - units) / (double)(waves * sms);
+    if (waste < best_waste - 1e-12) { best_waste = waste; best = s; }
+    if (waste <= 0.03) break;
+  }
+  return (int)best;
+}
+
+bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int flags, Plan* pl) {
+  int algo = flags & CCR_ALGO_MASK;
+  if (algo == CCR_ALGO_AUTO) algo = ccr_choose_algo(B, n_items, D, k);
+  const int sms = device_sm_count();
+  pl->algo = algo;
+  pl->C = cand_capacity(k);
+  if (algo == CCR_ALGO_TCGEN05) {
+    pl->n_q_tiles = (int)((B + kQTile - 1) / kQTile);
+    pl->rows_pad = pl->n_q_tiles * kQTile;
+    long long tiles = (n_items + kITile - 1) / kITile;
+    pl->S = splits_tc(pl->n_q_tiles, tiles, sms);
+  } else {
+    pl->n_q_tiles = (int)((B + kSimtRows - 1) / kSimtRows);
+    pl->rows_pad = pl->n_q_tiles * kSimtRows;
+    long long chunks = (n_items + kSimtChunk - 1) / kSimtChunk;
+    long long s = (2LL * sms + pl->n_q_tiles - 1) / pl->n_q_tiles;
+    if (s > chunks) s = chunks;
+    if (s < 1) s = 1;
+    pl->S = (int)s;
+  }
+  size_t off = 0;
+  pl->off_cand = off;   off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->C * sizeof(u64), 256);
+  pl->off_counts = off; off = align_up(off + (size_t)pl->rows_pad * pl->S * sizeof(int), 256);
+  pl->off_ovr_hi = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u64), 256);
+  pl->off_ovr_lo = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u32), 256);
+  pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
+  pl->total = off;
+  return true;
+}
+
+int check_shape(long long B, long long n_items, int D, int k, int flags) {
+  if (B < 0 || n_items < 0) return fail(CCR_EINVAL, "negative size B=%lld n_items=%lld", B, n_items);
+  if (B > (1LL << 24)) return fail(CCR_EUNSUPPORTED, "B=%lld > 2^24", B);
+  if (n_items > (1LL << 31) - 512) return fail(CCR_EUNSUPPORTED, "n_items=%lld per shard must be < 2^31", n_items);
+  if (D <= 0 || D % 8 != 0 || D > 4096) return fail(CCR_EUNSUPPORTED, "D=%d must be a multiple of 8 in [8,4096]", D);
+  if (k < 1 || k > CCR_MAX_K) return fail(CCR_EUNSUPPORTED, "k=%d outside [1,%d]", k, CCR_MAX_K);
+  if (k > n_items && !(flags & CCR_FLAG_ALLOW_SHORT))
+    return fail(CCR_EK_RANGE, "selected index k out of range (k=%d > n_items=%lld)", k, n_items);
+  int algo = flags & CCR_ALGO_MASK;
+  if (algo != CCR_ALGO_AUTO && algo != CCR_ALGO_SIMT && algo != CCR_ALGO_TCGEN05)
+    return fail(CCR_EINVAL, "unknown algo flag %d", algo);
+  return CCR_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ccr_abi_version(void) { return CCR_ABI_VERSION; }
+const char* ccr_last_error_string(void) { return g_err; }
+
+void ccr_debug_set_status_ptr(void* device_visible_ptr) { g_status_override = device_visible_ptr; }
+
+int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k) {
+  (void)n_items; (void)D; (void)k;
+  // B <= 8: one SIMT pass streams the table once with plain 128-bit loads; above that the
+  // tensor-core kernel reads it once for 128 rows at a time.
+  return B <= kSimtRows ? CCR_ALGO_SIMT : CCR_ALGO_TCGEN05;
+}
+
+size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int flags) {
+  if (check_shape(B, n_items, D, k, flags | CCR_FLAG_ALLOW_SHORT) != CCR_OK) return 0;
+  Plan pl;
+  make_plan(B, n_items, D, k, mask_nnz, flags, &pl);
+  return pl.total;
+}
+
+int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* info4) {
+  int rc = check_shape(B, n_items, D, k, flags | CCR_FLAG_ALLOW_SHORT);
+  if (rc) return rc;
+  if (!info4) return fail(CCR_EINVAL, "info4 is null");
+  Plan pl;
+  make_plan(B, n_items, D, k, 0, flags, &pl);
+  info4[0] = pl.n_q_tiles;
+  info4[1] = pl.S;
+  info4[2] = pl.C;
+  info4[3] = pl.algo;
+  return CCR_OK;
+}
+
+int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
+                        int64_t ldi, int D, int k, const int64_t* mask_indptr, const int32_t* mask_cols,
+                        const double* mask_vals, int64_t mask_nnz, int mask_mode, int64_t id_offset,
+                        float* out_scores,
+                        double* out_scores64, int64_t* out_ids, void* workspace, size_t workspace_bytes,
+                        int flags, void* stream) {
+  int rc = check_shape(B, n_items, D, k, flags);
+  if (rc) return rc;
+  if (B == 0) return CCR_OK;
+  if (!q || !out_ids) return fail(CCR_EINVAL, "null q / out_ids");
+  if (n_items > 0 && !items) return fail(CCR_EINVAL, "null items");
+  if (ldq < D || ldi < D || ldq % 8 || ldi % 8) return fail(CCR_EINVAL, "ldq/ldi must be >= D and multiples of 8");
+  if (((uintptr_t)q & 15) || ((uintptr_t)items & 15)) return fail(CCR_EINVAL, "q/items must be 16-byte aligned");
+  if (mask_mode != CCR_MASK_NONE && mask_mode != CCR_MASK_SET && mask_mode != CCR_MASK_ADD)
+    return fail(CCR_EINVAL, "bad mask_mode %d", mask_mode);
+  const bool has_mask = mask_mode != CCR_MASK_NONE && mask_indptr != nullptr;
+  if (has_mask && (!mask_cols || !mask_vals)) return fail(CCR_EINVAL, "mask_cols / mask_vals null");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  const long long nnz = has_mask ? mask_nnz : 0;
+  if (nnz < 0) return fail(CCR_EINVAL, "mask_nnz = %lld", nnz);
+  Plan pl;
+  make_plan(B, n_items, D, k, nnz, flags, &pl);
+  if (!workspace || workspace_bytes < pl.total)
+    return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, pl.total);
+  unsigned char* ws = (unsigned char*)workspace;
+  DeviceStatus* status = g_status_override ? (DeviceStatus*)g_status_override : (DeviceStatus*)(ws + pl.off_status);
+  cudaError_t e = cudaSuccess;
+  if (!g_status_override) e = cudaMemsetAsync(status, 0, sizeof(DeviceStatus), st);
+  if (e != cudaSuccess) return fail(CCR_ECUDA, "memset status: %s", cudaGetErrorString(e));
+
+  SelectParams sp;
+  sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B;
+  sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
+  sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles;
+  sp.mask_indptr = has_mask ? (const long long*)mask_indptr : nullptr;
+  sp.mask_cols = has_mask ? mask_cols : nullptr;
+  sp.cand = (u64*)(ws + pl.off_cand);
+  sp.counts = (int*)(ws + pl.off_counts);
+  sp.status = status;
+
+  int lr = 0;
+  if (n_items == 0) {
+    e = cudaMemsetAsync(sp.counts, 0, (size_t)pl.rows_pad * pl.S * sizeof(int), st);
+    if (e != cudaSuccess) return fail(CCR_ECUDA, "memset counts: %s", cudaGetErrorString(e));
+  } else if (pl.algo == CCR_ALGO_TCGEN05) {
+    lr = launch_select_tc(sp, st, device_sm_count());
+  } else {
+    lr = launch_select_simt(sp, st);
+  }
+  if (lr) return fail(CCR_ECUDA, "select kernel launch failed (%d: %s)", lr, lr > 0 ? cudaGetErrorString((cudaError_t)lr) : "tensor map");
+
+  if (has_mask && nnz > 0) {
+    OverrideParams op;
+    op.q = sp.q; op.ldq = ldq; op.B = (int)B; op.items = sp.items; op.ldi = ldi; op.n_items = n_items; op.D = D;
+    op.mask_indptr = sp.mask_indptr; op.mask_cols = mask_cols; op.mask_vals = mask_vals; op.nnz = nnz;
+    op.mode = mask_mode; op.ovr_hi = (u64*)(ws + pl.off_ovr_hi); op.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
+    lr = launch_overrides(op, st);
+    if (lr) return fail(CCR_ECUDA, "override kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  }
+
+  FinalizeParams fp;
+  fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S; fp.cand = sp.cand; fp.counts = sp.counts;
+  fp.mask_indptr = (has_mask && nnz > 0) ? sp.mask_indptr : nullptr;
+  fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
+  fp.id_offset = id_offset; fp.out_scores = out_scores; fp.out_scores64 = out_scores64;
+  fp.out_ids = (long long*)out_ids;
+  lr = launch_finalize(fp, st);
+  if (lr) return fail(CCR_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B, int k_in, int k_out,
+                   float* out_scores, double* out_scores64, int64_t* out_ids, void* stream) {
+  if (G < 1 || B < 0 || k_in < 1 || k_out < 1) return fail(CCR_EINVAL, "bad merge shape G=%d B=%lld k_in=%d k_out=%d", G, (long long)B, k_in, k_out);
+  if (B == 0) return CCR_OK;
+  if (!scores64 || !ids || !out_ids) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_merge_topk(scores64, (const long long*)ids, G, B, k_in, k_out, out_scores, out_scores64,
+                             (long long*)out_ids, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "merge kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_ingest_rows_f32(const float* src, int64_t n, int D, int64_t ld_src, void* dst, int64_t ld_dst,
+                        int normalize, void* stream) {
+  if (n < 0 || D <= 0 || ld_src < D || ld_dst < D) return fail(CCR_EINVAL, "bad ingest shape");
+  if (n == 0) return CCR_OK;
+  if (!src || !dst) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_ingest_f32(src, n, D, ld_src, (__nv_bfloat16*)dst, ld_dst, normalize, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "ingest kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_normalize_rows_bf16(const void* src, int64_t n, int D, int64_t ld_src, void* dst, int64_t ld_dst,
+                            void* stream) {
+  if (n < 0 || D <= 0 || ld_src < D || ld_dst < D) return fail(CCR_EINVAL, "bad normalize shape");
+  if (n == 0) return CCR_OK;
+  if (!src || !dst) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_normalize_bf16((const __nv_bfloat16*)src, n, D, ld_src, (__nv_bfloat16*)dst, ld_dst,
+                                 (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "normalize kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
+                        int64_t ldi, int D, float* out, int64_t ld_out, void* stream) {
+  if (B < 0 || n_items < 0 || D <= 0 || D % 8 || ldq < D || ldi < D || ldq % 8 || ldi % 8 || ld_out < n_items)
+    return fail(CCR_EINVAL, "bad dense shape");
+  if (B == 0 || n_items == 0) return CCR_OK;
+  if (!q || !items || !out) return fail(CCR_EINVAL, "null pointer");
+  if (B > 65535) return fail(CCR_EUNSUPPORTED, "dense B > 65535");
+  int lr = launch_dense_f32((const __nv_bfloat16*)q, B, ldq, (const __nv_bfloat16*)items, n_items, ldi, D, out,
+                            ld_out, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "dense kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,498 @@
+// CUDA-core kernels of the score-and-rank path:
+//   select_simt_kernel  : streaming score + mask-exclusion + running top-k, B <= 8 rows per pass
+//                         (bandwidth-bound small-query-batch regime; 128-bit coalesced loads)
+//   override_kernel     : exact scores of the sparse mask entries (set / add in float64)
+//   finalize_kernel     : per row, exact top-k of (unit candidates U mask overrides), sorted
+//   merge_topk_kernel   : G-way merge of per-shard sorted lists (multi-GPU exchange step)
+//   ingest / normalize / dense helpers
+#include "ccr_params.cuh"
+
+namespace ccr {
+
+// =======================================================================================
+// SIMT streaming select.  grid = (S, n_groups), block = 256 (8 warps).
+// Each block owns one item split and one group of 8 query rows.  Per block iteration it
+// scores 32 items x 8 rows: warp w takes items [4w, 4w+4), every lane accumulates a 1/32
+// slice of D for 4 items x 8 rows, a 5-step transpose-reduce leaves lane L holding the
+// complete dot product of (item L>>3, row L&7), which is then threshold-tested and
+// appended to the row's candidate buffer.  A row whose buffer is nearly full is pruned to
+// its exact top-k by one warp (radix select in place), raising the row's threshold.
+// =======================================================================================
+__global__ void __launch_bounds__(256, 2) select_simt_kernel(SelectParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int D = p.D;
+  float* qs = reinterpret_cast<float*>(smem_raw);  // [8][D]
+  __shared__ int s_cnt[kSimtRows];
+  __shared__ float s_tau_f[kSimtRows];
+  __shared__ u64 s_tau_key[kSimtRows];
+  __shared__ u32 s_hist[kSimtRows][256];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int split = blockIdx.x, group = blockIdx.y;
+  const int row0 = group * kSimtRows;
+
+  // stage the 8 query rows as fp32, laid out [row][half][chunk][4] so that the two float4
+  // reads of a lane's 8-element chunk are each contiguous across lanes (no bank conflicts)
+  const int chunks = D >> 3;
+  for (int i = tid; i < kSimtRows * D; i += 256) {
+    int r = i / D, d = i - r * D;
+    int row = row0 + r;
+    int c = d >> 3, h = (d >> 2) & 1, e = d & 3;
+    qs[((r * 2 + h) * chunks + c) * 4 + e] =
+        (row < p.B) ? __bfloat162float(p.q[(long long)row * p.ldq + d]) : 0.f;
+  }
+  if (tid < kSimtRows) {
+    s_cnt[tid] = 0;
+    s_tau_f[tid] = (row0 + tid < p.B) ? -INFINITY : INFINITY;
+    s_tau_key[tid] = 0ull;
+  }
+  __syncthreads();
+
+  long long per = (p.n_items + p.S - 1) / p.S;
+  per = (per + kSimtChunk - 1) / kSimtChunk * kSimtChunk;
+  const long long i0 = (long long)split * per;
+  long long i1 = i0 + per;
+  if (i1 > p.n_items) i1 = p.n_items;
+
+  const int my_item = lane >> 3, my_row = lane & 7;
+  const int grow = row0 + my_row;
+  u64* my_buf = p.cand + ((long long)grow * p.S + split) * p.C;
+  long long mbeg = 0, mend = 0;
+  if (p.mask_indptr && grow < p.B) { mbeg = p.mask_indptr[grow]; mend = p.mask_indptr[grow + 1]; }
+
+  for (long long base = i0; base < i1; base += kSimtChunk) {
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    const long long it0 = base + warp * 4;
+    for (int c = lane; c < chunks; c += 32) {
+      uint4 w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        long long it = it0 + j;
+        if (it < i1) w[j] = ldg_nc_v4(p.items + it * p.ldi + c * 8);
+        else w[j] = make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int r = 0; r < kSimtRows; ++r) {
+        const float4 qa = *reinterpret_cast<const float4*>(qs + ((r * 2 + 0) * chunks + c) * 4);
+        const float4 qb = *reinterpret_cast<const float4*>(qs + ((r * 2 + 1) * chunks + c) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = acc[j * 8 + r];
+          a = fmaf(bf16_lo(w[j].x), qa.x, a);
+          a = fmaf(bf16_hi(w[j].x), qa.y, a);
+          a = fmaf(bf16_lo(w[j].y), qa.z, a);
+          a = fmaf(bf16_hi(w[j].y), qa.w, a);
+          a = fmaf(bf16_lo(w[j].z), qb.x, a);
+          a = fmaf(bf16_hi(w[j].z), qb.y, a);
+          a = fmaf(bf16_lo(w[j].w), qb.z, a);
+          a = fmaf(bf16_hi(w[j].w), qb.w, a);
+          acc[j * 8 + r] = a;
+        }
+      }
+    }
+    // transpose-reduce: after step with offset o, lanes with bit o keep the upper half
+#pragma unroll
+    for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        float send = upper ? acc[i] : acc[i + n];
+        float keep = upper ? acc[i + n] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    const float s = acc[0];
+    const long long item = it0 + my_item;
+    if (item < i1 && s >= s_tau_f[my_row]) {
+      u64 key = make_key(s, (u32)item);
+      if (key > s_tau_key[my_row] &&
+          !(p.mask_cols && mask_contains(p.mask_cols, mbeg, mend, (int)item))) {
+        int pos = atomicAdd(&s_cnt[my_row], 1);
+        my_buf[pos] = key;  // pos < C: every row has >= 32 free slots at iteration start
+      }
+    }
+    int near_full = 0;
+    if (tid < kSimtRows) near_full = s_cnt[tid] > p.C - kSimtChunk;
+    if (__syncthreads_or(near_full)) {
+      if (warp < kSimtRows) {
+        int n = s_cnt[warp];
+        if (n > p.C - kSimtChunk) {
+          u64* b = p.cand + ((long long)(row0 + warp) * p.S + split) * p.C;
+          u64 pivot = warp_prune(b, n, p.k, s_hist[warp]);
+          if (lane == 0) {
+            s_cnt[warp] = p.k;
+            s_tau_key[warp] = pivot;
+            s_tau_f[warp] = key_score(pivot);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid < kSimtRows) p.counts[(long long)(row0 + tid) * p.S + split] = s_cnt[tid];
+}
+
+int launch_select_simt(const SelectParams& p, cudaStream_t st) {
+  size_t smem = (size_t)kSimtRows * p.D * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(select_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(p.S, p.n_q_tiles);
+  select_simt_kernel<<<grid, 256, smem, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// Mask overrides: one warp per CSR entry.  value = set ? v : double(q.item) + v.
+// =======================================================================================
+__global__ void __launch_bounds__(256) override_kernel(OverrideParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (e >= p.nnz) return;
+  // row of entry e: largest r with indptr[r] <= e
+  int lo = 0, hi = p.B;  // invariant: indptr[lo] <= e < indptr[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (p.mask_indptr[mid] <= e) lo = mid; else hi = mid;
+  }
+  const int row = lo;
+  const int col = p.mask_cols[e];
+  double val;
+  if (col < 0 || (long long)col >= p.n_items) {
+    if (lane == 0) { p.ovr_hi[e] = 0ull; p.ovr_lo[e] = 0u; }  // ignored by finalize (hi == 0)
+    return;
+  }
+  if (p.mode == 1) {
+    val = p.mask_vals[e];
+  } else {
+    float acc = 0.f;
+    const __nv_bfloat16* qr = p.q + (long long)row * p.ldq;
+    const __nv_bfloat16* ir = p.items + (long long)col * p.ldi;
+    for (int c = lane; c < (p.D >> 3); c += 32) {
+      uint4 a = *reinterpret_cast<const uint4*>(qr + c * 8);
+      uint4 b = ldg_nc_v4(ir + c * 8);
+      acc = fmaf(bf16_lo(a.x), bf16_lo(b.x), acc); acc = fmaf(bf16_hi(a.x), bf16_hi(b.x), acc);
+      acc = fmaf(bf16_lo(a.y), bf16_lo(b.y), acc); acc = fmaf(bf16_hi(a.y), bf16_hi(b.y), acc);
+      acc = fmaf(bf16_lo(a.z), bf16_lo(b.z), acc); acc = fmaf(bf16_hi(a.z), bf16_hi(b.z), acc);
+      acc = fmaf(bf16_lo(a.w), bf16_lo(b.w), acc); acc = fmaf(bf16_hi(a.w), bf16_hi(b.w), acc);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    val = (double)acc + p.mask_vals[e];
+  }
+  if (lane == 0) {
+    u64 h = ord64(val);
+    p.ovr_hi[e] = h ? h : 1ull;  // 0 is reserved for "invalid"
+    p.ovr_lo[e] = 0xFFFFFFFFu - (u32)col;
+  }
+}
+
+int launch_overrides(const OverrideParams& p, cudaStream_t st) {
+  if (p.nnz <= 0) return 0;
+  long long blocks = (p.nnz + 7) / 8;
+  override_kernel<<<(unsigned)blocks, 256, 0, st>>>(p);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// Finalize: one block (256 threads) per query row.
+// Entries: dense candidates of every split (64-bit keys) and the row's mask overrides, unified
+// as 96-bit sort keys (hi = ord64(double value), lo = ~id).  Exact k-th largest by MSB-first
+// radix select (<= 12 passes, early exit), winners gathered to shared memory, bitonic sorted,
+// written out.
+// =======================================================================================
+struct RowEntries {
+  const u64* cand; const int* counts; int S, C;
+  const u64* ovr_hi; const u32* ovr_lo; long long obeg, oend;
+  template <class F> __device__ __forceinline__ void for_each(F f) const {
+    for (int u = 0; u < S; ++u) {
+      int n = counts[u];
+      const u64* b = cand + (long long)u * C;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        u64 key = b[i];
+        f(ord64((double)key_score(key)), (u32)key);
+      }
+    }
+    for (long long e = obeg + threadIdx.x; e < oend; e += blockDim.x) {
+      u64 h = ovr_hi[e];
+      if (h) f(h, ovr_lo[e]);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /*pow2 >= k*/) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* s_hi = reinterpret_cast<u64*>(smem_raw);          // [P]
+  u32* s_lo = reinterpret_cast<u32*>(s_hi + P);           // [P]
+  __shared__ u32 hist[256];
+  __shared__ int s_total, s_nwin;
+  __shared__ u32 s_d, s_need, s_binc;
+
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  RowEntries E;
+  E.cand = p.cand + (long long)row * p.S * p.C;
+  E.counts = p.counts + (long long)row * p.S;
+  E.S = p.S; E.C = p.C;
+  E.ovr_hi = p.ovr_hi; E.ovr_lo = p.ovr_lo;
+  E.obeg = p.mask_indptr ? p.mask_indptr[row] : 0;
+  E.oend = p.mask_indptr ? p.mask_indptr[row + 1] : 0;
+
+  if (tid == 0) { s_total = 0; s_nwin = 0; }
+  for (int i = tid; i < P; i += 256) { s_hi[i] = 0ull; s_lo[i] = 0u; }
+  __syncthreads();
+  {
+    int local = 0;
+    E.for_each([&](u64, u32) { ++local; });
+    atomicAdd(&s_total, local);
+  }
+  __syncthreads();
+  const int total = s_total;
+  const int k = p.k;
+
+  u64 phi = 0, mhi = 0;  // prefix over hi
+  u32 plo = 0, mlo = 0;  // prefix over lo
+  bool select_all = total <= k;
+  if (!select_all) {
+    int need = k;
+    for (int pass = 0; pass < 12; ++pass) {
+      hist[tid] = 0;
+      __syncthreads();
+      const int sh = pass < 8 ? 56 - 8 * pass : 24 - 8 * (pass - 8);
+      E.for_each([&](u64 hi, u32 lo) {
+        if ((hi & mhi) == phi && (lo & mlo) == plo) {
+          u32 d = pass < 8 ? (u32)(hi >> sh) & 255u : (lo >> sh) & 255u;
+          atomicAdd(&hist[d], 1u);
+        }
+      });
+      __syncthreads();
+      if (warp == 0) {
+        u32 c[8], lane_sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; lane_sum += c[j]; }
+        u32 incl = lane_sum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          u32 t = __shfl_down_sync(0xffffffffu, incl, off);
+          if (lane + off < 32) incl += t;
+        }
+        u32 above = incl - lane_sum;
+        if (above < (u32)need && (u32)need <= incl) {
+          u32 run = above;
+          bool done = false;
+#pragma unroll
+          for (int j = 7; j >= 0; --j) {
+            if (!done) {
+              if (run + c[j] >= (u32)need) { s_d = lane * 8 + j; s_need = need - run; s_binc = c[j]; done = true; }
+              else run += c[j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      const u32 d = s_d;
+      need = (int)s_need;
+      if (pass < 8) { phi |= (u64)d << sh; mhi |= 0xFFull << sh; }
+      else { plo |= d << sh; mlo |= 0xFFu << sh; }
+      if (s_binc == (u32)need) break;  // every key in the bin is a winner: prefix is enough
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // winners: key > prefix-extended threshold.  With early exit the pivot is "all keys whose
+  // masked bits >= prefix", i.e. compare on the masked part only.
+  E.for_each([&](u64 hi, u32 lo) {
+    bool win;
+    if (select_all) win = true;
+    else {
+      u64 a = hi & mhi;
+      win = (a > phi) || (a == phi && (lo & mlo) >= plo);
+    }
+    if (win) {
+      int pos = atomicAdd(&s_nwin, 1);
+      if (pos < P) { s_hi[pos] = hi; s_lo[pos] = lo; }
+    }
+  });
+  __syncthreads();
+  // bitonic sort, descending by (hi, lo); padding entries are (0,0) = smallest
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += 256) {
+        int i = 2 * t - (t & (stride - 1));
+        int j = i + stride;
+        bool desc = ((i & size) == 0);
+        u64 hi_i = s_hi[i], hi_j = s_hi[j];
+        u32 lo_i = s_lo[i], lo_j = s_lo[j];
+        bool i_lt_j = (hi_i < hi_j) || (hi_i == hi_j && lo_i < lo_j);
+        if (i_lt_j == desc) { s_hi[i] = hi_j; s_hi[j] = hi_i; s_lo[i] = lo_j; s_lo[j] = lo_i; }
+      }
+      __syncthreads();
+    }
+  }
+  const int nwin = min(s_nwin, k);
+  for (int i = tid; i < k; i += 256) {
+    long long o = (long long)row * k + i;
+    if (i < nwin) {
+      double v = unord64(s_hi[i]);
+      if (p.out_scores) p.out_scores[o] = (float)v;
+      if (p.out_scores64) p.out_scores64[o] = v;
+      p.out_ids[o] = (long long)(0xFFFFFFFFu - s_lo[i]) + p.id_offset;
+    } else {
+      if (p.out_scores) p.out_scores[o] = -INFINITY;
+      if (p.out_scores64) p.out_scores64[o] = -INFINITY;
+      p.out_ids[o] = -1;
+    }
+  }
+}
+
+int launch_finalize(const FinalizeParams& p, cudaStream_t st) {
+  int P = 32;
+  while (P < p.k) P <<= 1;
+  size_t smem = (size_t)P * 12;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  finalize_kernel<<<p.B, 256, smem, st>>>(p, P);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// G-way merge of sorted runs (multi-GPU exchange step).  One block per row; every entry
+// finds its output rank by binary-searching each of the G runs.
+// order: score descending, then id ascending; id < 0 = padding (ignored).
+// =======================================================================================
+__device__ __forceinline__ bool precedes(double sa, long long ia, double sb, long long ib) {
+  return (sa > sb) || (sa == sb && ia < ib);
+}
+
+__global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restrict__ s,
+                                                         const long long* __restrict__ ids, int G,
+                                                         long long B, int k_in, int k_out, float* os,
+                                                         double* os64, long long* oi) {
+  const long long row = blockIdx.x;
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int local_valid = 0;
+  for (int e = threadIdx.x; e < G * k_in; e += blockDim.x) {
+    const int g = e / k_in, i = e - g * k_in;
+    const long long off = ((long long)g * B + row) * k_in;
+    const long long id = ids[off + i];
+    if (id < 0) continue;
+    ++local_valid;
+    const double sc = s[off + i];
+    int rank = 0;
+    for (int h = 0; h < G; ++h) {
+      const long long oh = ((long long)h * B + row) * k_in;
+      // number of valid entries of run h that precede (sc, id)
+      int lo = 0, hi = k_in;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        long long mid_id = ids[oh + mid];
+        bool before = (mid_id >= 0) && precedes(s[oh + mid], mid_id, sc, id);
+        if (before) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k_out) {
+      long long o = row * k_out + rank;
+      if (os) os[o] = (float)sc;
+      if (os64) os64[o] = sc;
+      oi[o] = id;
+    }
+  }
+  atomicAdd(&s_valid, local_valid);
+  __syncthreads();
+  for (int r = s_valid + threadIdx.x; r < k_out; r += blockDim.x) {
+    long long o = row * k_out + r;
+    if (os) os[o] = -INFINITY;
+    if (os64) os64[o] = -INFINITY;
+    oi[o] = -1;
+  }
+}
+
+int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,
+                      float* os, double* os64, long long* oi, cudaStream_t st) {
+  if (B == 0) return 0;
+  merge_topk_kernel<<<(unsigned)B, 256, 0, st>>>(s, ids, G, B, k_in, k_out, os, os64, oi);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// Table ingest / normalisation: one warp per row.
+// =======================================================================================
+template <typename SrcT>
+__global__ void __launch_bounds__(256) ingest_kernel(const SrcT* __restrict__ src, long long n, int D,
+                                                     long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                                     long long ld_dst, int normalize) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const SrcT* s = src + row * ld_src;
+  float scale = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { float v = (float)s[d]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+  }
+  __nv_bfloat16* o = dst + row * ld_dst;
+  for (int d = lane; d < ld_dst; d += 32) {
+    float v = d < D ? (float)s[d] * scale : 0.f;
+    o[d] = __float2bfloat16_rn(v);
+  }
+}
+
+int launch_ingest_f32(const float* src, long long n, int D, long long ld_src, __nv_bfloat16* dst,
+                      long long ld_dst, int normalize, cudaStream_t st) {
+  if (n == 0) return 0;
+  ingest_kernel<float><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(src, n, D, ld_src, dst, ld_dst, normalize);
+  return (int)cudaGetLastError();
+}
+int launch_normalize_bf16(const __nv_bfloat16* src, long long n, int D, long long ld_src,
+                          __nv_bfloat16* dst, long long ld_dst, cudaStream_t st) {
+  if (n == 0) return 0;
+  ingest_kernel<__nv_bfloat16><<<(unsigned)((n + 7) / 8), 256, 0, st>>>(src, n, D, ld_src, dst, ld_dst, 1);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// Dense fp32 score tile (not a hot path): one warp per (row, item).
+// =======================================================================================
+__global__ void __launch_bounds__(256) dense_kernel(const __nv_bfloat16* __restrict__ q, long long B,
+                                                    long long ldq, const __nv_bfloat16* __restrict__ items,
+                                                    long long n, long long ldi, int D,
+                                                    float* __restrict__ out, long long ld_out) {
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long row = blockIdx.y;
+  if (item >= n) return;
+  const __nv_bfloat16* qr = q + row * ldq;
+  const __nv_bfloat16* ir = items + item * ldi;
+  float acc = 0.f;
+  for (int c = lane; c < (D >> 3); c += 32) {
+    uint4 a = *reinterpret_cast<const uint4*>(qr + c * 8);
+    uint4 b = *reinterpret_cast<const uint4*>(ir + c * 8);
+    acc = fmaf(bf16_lo(a.x), bf16_lo(b.x), acc); acc = fmaf(bf16_hi(a.x), bf16_hi(b.x), acc);
+    acc = fmaf(bf16_lo(a.y), bf16_lo(b.y), acc); acc = fmaf(bf16_hi(a.y), bf16_hi(b.y), acc);
+    acc = fmaf(bf16_lo(a.z), bf16_lo(b.z), acc); acc = fmaf(bf16_hi(a.z), bf16_hi(b.z), acc);
+    acc = fmaf(bf16_lo(a.w), bf16_lo(b.w), acc); acc = fmaf(bf16_hi(a.w), bf16_hi(b.w), acc);
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) out[row * ld_out + item] = acc;
+}
+
+int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const __nv_bfloat16* items,
+                     long long n, long long ldi, int D, float* out, long long ld_out, cudaStream_t st) {
+  if (B == 0 || n == 0) return 0;
+  dim3 grid((unsigned)((n + 7) / 8), (unsigned)B);
+  dense_kernel<<<grid, 256, 0, st>>>(q, B, ldq, items, n, ldi, D, out, ld_out);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace ccr

@@ -1,0 +1,144 @@
+/*
+ * ccr_b200.h -- C ABI of the B200-native candidate score-and-rank path.
+ *
+ * The reference (awslabs/crowd-coachable-recommendations) has no FFI: its "operator API"
+ * for this path is three Python call sites that run stock torch ops.  Each entry point
+ * below replaces one of those torch call sites; the Python host layer
+ * (crowd-coachable-recommendations_b200/ccr_b200) binds them with ctypes and keeps the
+ * reference's Python signatures.  Reference paths are relative to /root/reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer, including the workspace; the library allocates no
+ *     persistent device memory and never synchronises the stream;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream);
+ *   - return value: 0 on success, negative CCR_E* on failure; ccr_last_error_string()
+ *     returns a thread-local description of the last failure;
+ *   - re-entrant and stream-ordered; no global mutable state besides a per-device cache of
+ *     immutable device attributes.
+ */
+#ifndef CCR_B200_H_
+#define CCR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCR_ABI_VERSION 1
+
+/* error codes */
+#define CCR_OK 0
+#define CCR_EINVAL (-1)       /* bad argument (null pointer, misalignment, negative size...) */
+#define CCR_EUNSUPPORTED (-2) /* shape outside what the kernels implement (k too large, D...) */
+#define CCR_EWORKSPACE (-3)   /* workspace_bytes smaller than ccr_score_topk_workspace_bytes() */
+#define CCR_ECUDA (-4)        /* a CUDA runtime / driver call failed                          */
+#define CCR_EK_RANGE (-5)     /* k > number of items ("selected index k out of range")         */
+
+/* mask_mode */
+#define CCR_MASK_NONE 0
+#define CCR_MASK_SET 1 /* score[row, col] = val   -- ranking(): scores[block_ind] = -1e6,
+                          scripts/ms_marco_eval.py:227                                         */
+#define CCR_MASK_ADD 2 /* score[row, col] += val in float64 -- rime_lite prior_score:
+                          src/rime_lite/dataset/base.py:234,279-282 added at
+                          src/ccrec/models/bert_mt.py:376 / score_array.py:120-121,291-293     */
+
+/* flags for ccr_score_topk_bf16 */
+#define CCR_ALGO_AUTO 0
+#define CCR_ALGO_SIMT 1   /* CUDA-core streaming kernel (128-bit coalesced loads); any B, meant
+                             for the bandwidth-bound B <= 8 regime                              */
+#define CCR_ALGO_TCGEN05 2 /* TMA + tcgen05/TMEM bf16 GEMM fused with mask + top-k epilogue    */
+#define CCR_ALGO_MASK 0xF
+#define CCR_FLAG_ALLOW_SHORT 0x10 /* k > n_items allowed: tail padded with (-inf, id -1); used for
+                                     row shards smaller than k                                  */
+
+#define CCR_MAX_K 2048
+
+int ccr_abi_version(void);
+const char* ccr_last_error_string(void);
+
+/*
+ * Fused  scores = Q . items^T  ->  sparse mask  ->  per-row top-k, sorted descending,
+ * ties broken by lowest item id.  The B x N score matrix is never written to memory.
+ *
+ * Replaces, in one call:
+ *   scripts/ms_marco_eval.py:206-218  (tile GEMM loop + D2H scatter into the host matrix)
+ *   scripts/ms_marco_eval.py:221-230  (host mask, H2D of the row, full sort, [:1001])
+ *   src/rime_lite/util/__init__.py:135-141 (as_tensor of MatMul+prior, topk(k).indices)
+ *   src/ccrec/models/bbpr.py:528-545  (BertBPR.transform tile loop)
+ *
+ *   q        [B, ldq]  bf16 row-major queries / user embeddings (ldq >= D, ldq % 8 == 0)
+ *   items    [n_items, ldi] bf16 row-major item / passage table shard (ldi >= D, ldi % 8 == 0,
+ *            base 16-byte aligned)
+ *   D        embedding dim (768 in the reference: ms_marco_eval.py:190), D % 8 == 0, D <= 4096
+ *   k        1 .. CCR_MAX_K
+ *   mask_*   CSR over the LOCAL item columns of this shard: indptr[B+1] (int64), cols sorted
+ *            and unique per row (int32, < n_items), vals float64, mask_nnz == indptr[B]; all
+ *            NULL / 0 when mask_mode == CCR_MASK_NONE
+ *   id_offset added to local item ids on output (row-sharded tables)
+ *   out_scores   [B, k] float32, descending           (may be NULL)
+ *   out_scores64 [B, k] float64 exact value the order was decided on (may be NULL)
+ *   out_ids      [B, k] int64 global item ids
+ */
+int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq,
+                        const void* items, int64_t n_items, int64_t ldi,
+                        int D, int k,
+                        const int64_t* mask_indptr, const int32_t* mask_cols,
+                        const double* mask_vals, int64_t mask_nnz, int mask_mode,
+                        int64_t id_offset,
+                        float* out_scores, double* out_scores64, int64_t* out_ids,
+                        void* workspace, size_t workspace_bytes,
+                        int flags, void* stream);
+
+/* Bytes of workspace ccr_score_topk_bf16 needs for these arguments (same flags!).
+ * Returns 0 on invalid arguments. */
+size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k,
+                                      int64_t mask_nnz, int flags);
+
+/*
+ * G-way merge of per-shard top-k lists after the all-gather (multi-GPU exchange step; no
+ * reference counterpart -- the reference scores on one GPU, ms_marco_eval.py:205).
+ *   scores64 [G, B, k_in] float64 each run sorted descending, ids [G, B, k_in] int64
+ *   (id < 0 = padding).  Output: the k_out best of the union per row, descending,
+ *   ties -> lowest id.  Missing entries are padded with (-inf, -1).
+ */
+int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B, int k_in,
+                   int k_out, float* out_scores, double* out_scores64, int64_t* out_ids,
+                   void* stream);
+
+/*
+ * Embedding-table ingest: fp32 rows -> bf16 table rows, optionally L2-normalised first
+ * (F.normalize(p=2, dim=1, eps=1e-12) in fp32, then round) for CCREC_SIM_TYPE=cos.
+ * Replaces `.to("cpu")` in scripts/ms_marco_eval.py:140-145 and cos_sim's normalisation
+ * (scripts/ms_marco_eval.py:160-161, src/ccrec/models/bbpr.py:490-491).
+ *   src [n, ld_src] float32, dst [n, ld_dst] bf16; columns D..ld_dst-1 of dst are zeroed.
+ */
+int ccr_ingest_rows_f32(const float* src, int64_t n, int D, int64_t ld_src,
+                        void* dst, int64_t ld_dst, int normalize, void* stream);
+
+/* Same for rows that are already bf16 (normalisation computed in fp32). */
+int ccr_normalize_rows_bf16(const void* src, int64_t n, int D, int64_t ld_src,
+                            void* dst, int64_t ld_dst, void* stream);
+
+/*
+ * Dense score tile  out[B, n] = Q . items^T  (fp32) for callers that really want the matrix
+ * (LazyScore.as_tensor on small reranking sets: score_array.py:291-293).  CUDA-core kernel,
+ * not a hot path.
+ */
+int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
+                        int64_t ldi, int D, float* out, int64_t ld_out, void* stream);
+
+/* Which kernel ccr_score_topk_bf16 picks under CCR_ALGO_AUTO: CCR_ALGO_SIMT or CCR_ALGO_TCGEN05. */
+int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k);
+
+/* Launch geometry of the last-configured plan, for benchmarks / DESIGN.md bookkeeping:
+ * fills n_q_tiles, n_splits, cand_capacity, n_launches.  Returns 0 or CCR_E*. */
+int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* info4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCR_B200_H_ */
