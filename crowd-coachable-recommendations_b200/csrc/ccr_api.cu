@@ -1,6 +1,7 @@
 // C ABI (include/ccr_b200.h): argument validation, launch planning, workspace carving.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/ccr_b200.h"
@@ -39,7 +40,8 @@ struct Plan {
   int algo;
   int n_q_tiles;  // TC: query tiles of 128; SIMT: groups of 8
   int rows_pad;
-  int S;
+  int S;        // item splits
+  int halves;   // candidate buffers per (row, split): 2 for the tensor-core kernel
   int C;
   size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, total;
 };
@@ -73,21 +75,25 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
   pl->C = cand_capacity(k);
   if (algo == CCR_ALGO_TCGEN05) {
     pl->n_q_tiles = (int)((B + kQTile - 1) / kQTile);
+    if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
     pl->rows_pad = pl->n_q_tiles * kQTile;
     long long tiles = (n_items + kITile - 1) / kITile;
     pl->S = splits_tc(pl->n_q_tiles, tiles, sms);
+    pl->halves = 2;
   } else {
     pl->n_q_tiles = (int)((B + kSimtRows - 1) / kSimtRows);
+    if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
     pl->rows_pad = pl->n_q_tiles * kSimtRows;
     long long chunks = (n_items + kSimtChunk - 1) / kSimtChunk;
     long long s = (2LL * sms + pl->n_q_tiles - 1) / pl->n_q_tiles;
     if (s > chunks) s = chunks;
     if (s < 1) s = 1;
     pl->S = (int)s;
+    pl->halves = 1;
   }
   size_t off = 0;
-  pl->off_cand = off;   off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->C * sizeof(u64), 256);
-  pl->off_counts = off; off = align_up(off + (size_t)pl->rows_pad * pl->S * sizeof(int), 256);
+  pl->off_cand = off;   off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * pl->C * sizeof(u64), 256);
+  pl->off_counts = off; off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(int), 256);
   pl->off_ovr_hi = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u64), 256);
   pl->off_ovr_lo = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u32), 256);
   pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
@@ -184,10 +190,11 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.cand = (u64*)(ws + pl.off_cand);
   sp.counts = (int*)(ws + pl.off_counts);
   sp.status = status;
+  { const char* d = getenv("CCR_DEBUG"); sp.debug = d ? atoi(d) : 0; }
 
   int lr = 0;
   if (n_items == 0) {
-    e = cudaMemsetAsync(sp.counts, 0, (size_t)pl.rows_pad * pl.S * sizeof(int), st);
+    e = cudaMemsetAsync(sp.counts, 0, (size_t)pl.rows_pad * pl.S * pl.halves * sizeof(int), st);
     if (e != cudaSuccess) return fail(CCR_ECUDA, "memset counts: %s", cudaGetErrorString(e));
   } else if (pl.algo == CCR_ALGO_TCGEN05) {
     lr = launch_select_tc(sp, st, device_sm_count());
@@ -206,7 +213,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   }
 
   FinalizeParams fp;
-  fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S; fp.cand = sp.cand; fp.counts = sp.counts;
+  fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S * pl.halves; fp.cand = sp.cand; fp.counts = sp.counts;
   fp.mask_indptr = (has_mask && nnz > 0) ? sp.mask_indptr : nullptr;
   fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
   fp.id_offset = id_offset; fp.out_scores = out_scores; fp.out_scores64 = out_scores64;

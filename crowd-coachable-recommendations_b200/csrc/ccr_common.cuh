@@ -77,28 +77,52 @@ __device__ __forceinline__ bool mask_contains(const int* __restrict__ cols, long
 }
 
 // ---------------------------------------------------------------------------------------
-// Warp-cooperative exact selection on a buffer of n unique 64-bit keys in global memory.
-// Returns the `kth` largest key (1-based).  hist: 256 x u32 of shared memory private to the
-// warp.  MSB-first 8-bit radix select with early exit once the target bin holds one key.
-// All 32 lanes must call it with identical arguments.
+// explicit shared-memory accessors (32-bit shared addresses): keeps the selection code on
+// LDS / STS / ATOMS instead of generic LD / ST / ATOM when pointers lose their address space
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ u64 warp_select_kth(const u64* buf, int n, int kth, u32* hist) {
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sm_red_inc(u32 a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ u32 sm_ld32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sm_st32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ u64 sm_ld64(u32 a) { u64 v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sm_st64(u32 a, u64 v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+
+struct GlobalKeys {
+  u64* p;
+  __device__ __forceinline__ u64 get(int i) const { return p[i]; }
+  __device__ __forceinline__ void set(int i, u64 v) const { p[i] = v; }
+};
+struct SharedKeys {
+  u32 s;
+  __device__ __forceinline__ u64 get(int i) const { return sm_ld64(s + (u32)i * 8u); }
+  __device__ __forceinline__ void set(int i, u64 v) const { sm_st64(s + (u32)i * 8u, v); }
+};
+
+// ---------------------------------------------------------------------------------------
+// Warp-cooperative exact selection on n unique 64-bit keys.  Returns the `kth` largest key
+// (1-based).  hist_s: shared address of 256 x u32 private to the warp.  MSB-first 8-bit radix
+// select with early exit once the target bin holds one key.  All 32 lanes call it with
+// identical arguments.
+// ---------------------------------------------------------------------------------------
+template <class Keys>
+__device__ __forceinline__ u64 warp_select_kth(Keys keys, int n, int kth, u32 hist_s) {
   const int lane = threadIdx.x & 31;
   u64 prefix = 0, pmask = 0;
   int need = kth;
   for (int shift = 56; shift >= 0; shift -= 8) {
-    for (int i = lane; i < 256; i += 32) hist[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm_st32(hist_s + (u32)(lane * 8 + j) * 4u, 0u);
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
-      u64 key = buf[i];
-      if ((key & pmask) == prefix) atomicAdd(&hist[(u32)(key >> shift) & 255u], 1u);
+      u64 key = keys.get(i);
+      if ((key & pmask) == prefix) sm_red_inc(hist_s + ((u32)(key >> shift) & 255u) * 4u);
     }
     __syncwarp();
     // lane L owns digits [8L, 8L+8); higher lanes = higher digits
     u32 c[8];
     u32 lane_sum = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; lane_sum += c[j]; }
+    for (int j = 0; j < 8; ++j) { c[j] = sm_ld32(hist_s + (u32)(lane * 8 + j) * 4u); lane_sum += c[j]; }
     u32 incl = lane_sum;  // sum over lanes >= lane
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -131,7 +155,7 @@ __device__ __forceinline__ u64 warp_select_kth(const u64* buf, int n, int kth, u
       // unique key with this prefix: find it
       u64 found = 0;
       for (int i = lane; i < n; i += 32) {
-        u64 key = buf[i];
+        u64 key = keys.get(i);
         if ((key & pmask) == prefix) found = key;
       }
 #pragma unroll
@@ -145,30 +169,53 @@ __device__ __forceinline__ u64 warp_select_kth(const u64* buf, int n, int kth, u
   return prefix;
 }
 
-// Keep only keys >= pivot, compacted to the front of buf (stable).  Returns the kept count.
-__device__ __forceinline__ int warp_compact_ge(u64* buf, int n, u64 pivot) {
+// Keep only keys >= pivot: src[0,n) -> dst[0, kept), stable.  dst may alias src (in place).
+template <class Src, class Dst>
+__device__ __forceinline__ int warp_compact_ge(Src src, Dst dst, int n, u64 pivot) {
   const int lane = threadIdx.x & 31;
   int base = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
     int i = i0 + lane;
-    u64 key = (i < n) ? buf[i] : 0ull;
+    u64 key = (i < n) ? src.get(i) : 0ull;
     bool keep = (i < n) && (key >= pivot);
     unsigned m = __ballot_sync(0xffffffffu, keep);
     __syncwarp();
-    if (keep) buf[base + __popc(m & ((1u << lane) - 1u))] = key;
+    if (keep) dst.set(base + __popc(m & ((1u << lane) - 1u)), key);
     base += __popc(m);
     __syncwarp();
   }
   return base;
 }
 
-// prune a buffer down to its top-k; returns pivot (k-th largest key)
-__device__ __forceinline__ u64 warp_prune(u64* buf, int n, int k, u32* hist) {
+// Prune a candidate buffer in global memory down to its exact top-k; returns the pivot (k-th
+// largest key).  With stage_s != 0 the keys are first copied to that shared-memory staging area
+// (>= n keys) so the radix passes run at shared-memory latency.
+__device__ __forceinline__ u64 warp_prune(u64* buf, int n, int k, u32 hist_s, u32 stage_s) {
+  const int lane = threadIdx.x & 31;
   __syncwarp();
-  u64 pivot = warp_select_kth(buf, n, k, hist);
-  warp_compact_ge(buf, n, pivot);
+  u64 pivot;
+  if (stage_s) {
+    for (int i = lane; i < n; i += 32) sm_st64(stage_s + (u32)i * 8u, buf[i]);
+    __syncwarp();
+    pivot = warp_select_kth(SharedKeys{stage_s}, n, k, hist_s);
+    warp_compact_ge(SharedKeys{stage_s}, GlobalKeys{buf}, n, pivot);
+  } else {
+    pivot = warp_select_kth(GlobalKeys{buf}, n, k, hist_s);
+    warp_compact_ge(GlobalKeys{buf}, GlobalKeys{buf}, n, pivot);
+  }
   __syncwarp();
   return pivot;
+}
+
+// Append one candidate (noinline: keeps the unrolled per-column hit tests small).
+static __device__ __noinline__ int cand_insert(float s, u32 col, int cnt, u64 tau_key, u64* buf,
+                                        const int* mask_cols, long long mbeg, long long mend) {
+  const u64 key = make_key(s, col);
+  if (key > tau_key && !(mask_cols && mask_contains(mask_cols, mbeg, mend, (int)col))) {
+    buf[cnt] = key;
+    return cnt + 1;
+  }
+  return cnt;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256, 2) select_simt_kernel(SelectParams p) {
         int n = s_cnt[warp];
         if (n > p.C - kSimtChunk) {
           u64* b = p.cand + ((long long)(row0 + warp) * p.S + split) * p.C;
-          u64 pivot = warp_prune(b, n, p.k, s_hist[warp]);
+          u64 pivot = warp_prune(b, n, p.k, smem_addr(s_hist[warp]), 0u);
           if (lane == 0) {
             s_cnt[warp] = p.k;
             s_tau_key[warp] = pivot;

@@ -24,6 +24,7 @@ struct SelectParams {
   u64* cand;
   int* counts;
   DeviceStatus* status;
+  int debug;  // CCR_DEBUG bits (env, diagnostics only): 1 = skip selection, keep pipeline
 };
 
 struct FinalizeParams {

@@ -14,6 +14,7 @@
 // Persistent: grid = #SMs, each CTA walks units (query tile, item split) round-robin with the
 // query tile varying fastest so CTAs running concurrently share item tiles through L2.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ccr_params.cuh"
 
@@ -23,7 +24,9 @@ constexpr int kStages = 4;
 constexpr int kBytesA = kQTile * kKBlock * 2;   // 16384
 constexpr int kBytesB = kITile * kKBlock * 2;   // 32768
 constexpr int kStageBytes = kBytesA + kBytesB;  // 49152
-constexpr int kTcThreads = 192;                 // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, one per column half
+constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kStageKeys = 256;                 // candidate buffers up to this size are pruned in smem
 constexpr int kTmemCols = 512;
 constexpr unsigned long long kWaitLimitNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
 
@@ -34,7 +37,8 @@ struct __align__(8) TcShared {
   u64 tmem_empty[2];
   u32 tmem_base;
   u32 pad;
-  u32 hist[4][256];
+  u32 hist[kEpiWarps][256];
+  u64 stage[kEpiWarps][kStageKeys];
 };
 constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + sizeof(TcShared) + 1024;
 
@@ -128,6 +132,59 @@ __device__ __forceinline__ u64 make_sw128_desc(u32 saddr) {
 constexpr u32 kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kITile >> 3) << 17) | ((u32)(kQTile >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------
+// per-thread selection state and the per-chunk filter (32 columns of one query row)
+// ---------------------------------------------------------------------------------------
+struct SelState {
+  u64* buf;        // this (row, split, half)'s candidate buffer
+  int cnt;
+  float tau_f;     // score of the current k-th best (or -inf / +inf for padding rows)
+  u64 tau_key;
+  long long mbeg, mend;  // the row's slice of the mask CSR
+};
+
+__device__ __forceinline__ float max8(const u32 (&v)[32], int g) {
+  const float a = fmaxf(fmaxf(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1])), __uint_as_float(v[g * 8 + 2]));
+  const float b = fmaxf(fmaxf(__uint_as_float(v[g * 8 + 3]), __uint_as_float(v[g * 8 + 4])), __uint_as_float(v[g * 8 + 5]));
+  const float c = fmaxf(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+  return fmaxf(fmaxf(a, b), c);
+}
+
+__device__ __forceinline__ void select_chunk(const u32 (&v)[32], long long col0, SelState& st, const SelectParams& p,
+                                             int k, int C, u32 hist_s, u32 stage_s) {
+  const int lane = threadIdx.x & 31;
+  if (p.debug & 1) return;
+  float m8[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) m8[g] = max8(v, g);
+  const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  if (!__any_sync(0xffffffffu, m >= st.tau_f)) return;
+  // slow path: some row of this warp has a candidate in these 32 columns
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (m8[g] >= st.tau_f) {
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float s = __uint_as_float(v[g * 8 + jj]);
+        if (s >= st.tau_f) {
+          const long long col = col0 + g * 8 + jj;
+          if (col < p.n_items)
+            st.cnt = cand_insert(s, (u32)col, st.cnt, st.tau_key, st.buf, p.mask_cols, st.mbeg, st.mend);
+        }
+      }
+    }
+  }
+  unsigned need = __ballot_sync(0xffffffffu, st.cnt > C - 32);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    u64* b = reinterpret_cast<u64*>(__shfl_sync(0xffffffffu, (u64)(uintptr_t)st.buf, src));
+    const int n = __shfl_sync(0xffffffffu, st.cnt, src);
+    const u64 pivot = warp_prune(b, n, k, hist_s, stage_s);
+    if (lane == src) { st.cnt = k; st.tau_key = pivot; st.tau_f = key_score(pivot); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -145,7 +202,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full[s], 1); mbar_init(&sh->tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full[s], 1); mbar_init(&sh->tmem_empty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_items) : "memory");
@@ -211,73 +268,53 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else {
-    // ================= epilogue / selection: 4 warps, thread == query row =================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===== epilogue / selection: 8 warps; thread == (query row, 128-column half of the tile) =====
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+    const int half = ew >> 2;    // 0: tile columns [0,128), 1: [128,256)
     const int row_in_tile = quad * 32 + lane;
-    u32* hist = sh->hist[warp - 2];
-    int acc = 0; u32 acc_phase = 0;
+    const u32 hist_s = smem_addr(sh->hist[ew]);
     const int k = p.k, C = p.C;
+    const u32 stage_s = (C <= kStageKeys) ? smem_addr(sh->stage[ew]) : 0u;
+    int acc = 0; u32 acc_phase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
       const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
       const int row = qt * kQTile + row_in_tile;
       const bool valid_row = row < p.B;
-      u64* buf = p.cand + ((long long)row * p.S + u) * C;
-      int cnt = 0;
-      float tau_f = valid_row ? -INFINITY : INFINITY;
-      u64 tau_key = 0ull;
-      long long mbeg = 0, mend = 0;
-      if (p.mask_indptr && valid_row) { mbeg = p.mask_indptr[row]; mend = p.mask_indptr[row + 1]; }
+      SelState st;
+      st.buf = p.cand + (((long long)row * p.S + u) * 2 + half) * C;
+      st.cnt = 0;
+      st.tau_f = valid_row ? -INFINITY : INFINITY;
+      st.tau_key = 0ull;
+      st.mbeg = 0; st.mend = 0;
+      if (p.mask_indptr && valid_row) { st.mbeg = p.mask_indptr[row]; st.mend = p.mask_indptr[row + 1]; }
 
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&sh->tmem_full[acc], acc_phase, p.status, 400 + acc);
         tc_fence_after();
-        const u32 taddr0 = tmem_base + ((u32)(quad * 32) << 16) + (u32)(acc * kITile);
-        const long long col_tile = t * kITile;
-#pragma unroll 1
-        for (int c = 0; c < kITile / 32; ++c) {
-          u32 v[32];
-          tmem_ld_32x32b_x32(taddr0 + (u32)(c * 32), v);
-          tmem_ld_wait();
-          float m = __uint_as_float(v[0]);
-#pragma unroll
-          for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-          const bool hit = m >= tau_f;
-          if (__any_sync(0xffffffffu, hit)) {
-            if (hit) {
-              const long long col0 = col_tile + c * 32;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float s = __uint_as_float(v[j]);
-                if (s >= tau_f) {
-                  const long long col = col0 + j;
-                  if (col < p.n_items) {
-                    const u64 key = make_key(s, (u32)col);
-                    if (key > tau_key && !(p.mask_cols && mask_contains(p.mask_cols, mbeg, mend, (int)col))) {
-                      buf[cnt++] = key;
-                    }
-                  }
-                }
-              }
-            }
-            unsigned need = __ballot_sync(0xffffffffu, cnt > C - 32);
-            while (need) {
-              const int src = __ffs(need) - 1;
-              need &= need - 1;
-              u64* b = reinterpret_cast<u64*>(__shfl_sync(0xffffffffu, (u64)(uintptr_t)buf, src));
-              const int n = __shfl_sync(0xffffffffu, cnt, src);
-              const u64 pivot = warp_prune(b, n, k, hist);
-              if (lane == src) { cnt = k; tau_key = pivot; tau_f = key_score(pivot); }
-            }
-          }
-        }
-        // accumulator drained: hand it back to the MMA warp
+        const u32 taddr0 = tmem_base + ((u32)(quad * 32) << 16) + (u32)(acc * kITile + half * 128);
+        const long long col0 = t * kITile + half * 128;
+        u32 va[32], vb[32];
+        tmem_ld_32x32b_x32(taddr0, va);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr0 + 32, vb);
+        select_chunk(va, col0, st, p, k, C, hist_s, stage_s);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr0 + 64, va);
+        select_chunk(vb, col0 + 32, st, p, k, C, hist_s, stage_s);
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr0 + 96, vb);
+        select_chunk(va, col0 + 64, st, p, k, C, hist_s, stage_s);
+        tmem_ld_wait();
+        // every column of this half is in registers: hand the accumulator back to the MMA warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
+        select_chunk(vb, col0 + 96, st, p, k, C, hist_s, stage_s);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      p.counts[(long long)row * p.S + u] = cnt;
+      p.counts[((long long)row * p.S + u) * 2 + half] = st.cnt;
     }
   }
 
@@ -334,6 +371,7 @@ int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms) {
   if (e != cudaSuccess) return (int)e;
   int n_units = p.n_q_tiles * p.S;
   int grid = n_units < num_sms ? n_units : num_sms;
+  if (const char* g = getenv("CCR_DEBUG_GRID")) { int v = atoi(g); if (v > 0 && v < grid) grid = v; }
   if (grid < 1) grid = 1;
   select_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tq, ti, p);
   return (int)cudaGetLastError();

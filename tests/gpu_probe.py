@@ -60,7 +60,7 @@ def run_case(c):
     mask = None
     if c["mask"]:
         rs = np.random.RandomState(5)
-        rows = [rs.choice(N, size=min(N, rs.randint(0, 65)), replace=False) for _ in range(B)]
+        rows = [np.unique(rs.randint(0, N, size=min(N, rs.randint(0, 65)))) for _ in range(B)]
         if c["mask"] == 1:
             mask = engine.SparseMask.from_lists(rows, N, -1e6, engine.MASK_SET, dev)
         else:

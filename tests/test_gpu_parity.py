@@ -117,7 +117,11 @@ def test_ranking_dropin_vs_golden(ccr, name, golden_dir, monkeypatch):
     order = np.array([[pos[p] for p in prof[q].keys()] for q in qids])
     scores = np.array([list(prof[q].values()) for q in qids])
     assert order.shape == g["order"].shape
-    errs = O.check_topk(scores, order, ref_scores=g["scores"], ref_ids=g["order"], rtol=RTOL, atol=2e-2)
+    # the golden is the reference's fp32 arithmetic on UNROUNDED inputs; the device table is
+    # bf16, so the tolerance is 1e-2 relative to the scale of the live (unblocked) scores
+    live = g["scores"][g["scores"] > -1e6]
+    errs = O.check_topk(scores, order, ref_scores=g["scores"], ref_ids=g["order"], rtol=RTOL,
+                        atol=RTOL * float(np.abs(live).max()))
     assert not errs, errs[:5]
     # blocked passages carry exactly -1e6
     if c["block_dict"] is not None:
