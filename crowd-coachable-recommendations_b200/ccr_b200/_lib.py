@@ -28,6 +28,7 @@ EXPORTS = [
     "ccr_score_dense_f32",
     "ccr_choose_algo",
     "ccr_plan_info",
+    "ccr_set_profile_events",
 ]
 
 _lib = None
@@ -70,6 +71,8 @@ def lib():
     L.ccr_score_dense_f32.argtypes = [vp, i64, i64, vp, i64, i64, i32, vp, i64, vp]
     L.ccr_choose_algo.restype = i32
     L.ccr_choose_algo.argtypes = [i64, i64, i32, i32]
+    L.ccr_set_profile_events.restype = None
+    L.ccr_set_profile_events.argtypes = [vp, vp]
     L.ccr_plan_info.restype = i32
     L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i32, c.POINTER(c.c_int32)]
     if L.ccr_abi_version() != 1:

@@ -64,6 +64,20 @@ class SparseMask:
         self.vals = torch.as_tensor(self.host[2]).to(self.device)
 
     @classmethod
+    def from_device_tensors(cls, indptr, cols, vals, host, n_cols, mode):
+        """Wrap CSR arrays that are already (being copied) on the device; ``host`` holds the same
+        arrays as numpy for the host-side slicing helpers."""
+        self = cls.__new__(cls)
+        self.n_rows = int(indptr.shape[0]) - 1
+        self.n_cols = int(n_cols)
+        self.mode = mode
+        self.host = host
+        self.nnz = int(host[0][-1])
+        self.device = indptr.device
+        self.indptr, self.cols, self.vals = indptr, cols, vals
+        return self
+
+    @classmethod
     def from_scipy(cls, csr, mode, device):
         import scipy.sparse as sps
 

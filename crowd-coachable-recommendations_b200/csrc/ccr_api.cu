@@ -11,6 +11,7 @@ using namespace ccr;
 
 static thread_local char g_err[512] = "";
 static void* g_status_override = nullptr;  // diagnostics: host-mapped DeviceStatus (tests only)
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;  // see ccr_set_profile_events
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -43,7 +44,12 @@ struct Plan {
   int S;        // item splits
   int halves;   // candidate buffers per (row, split): 2 for the tensor-core kernel
   int C;
-  size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, total;
+  int share_j, share_m;  // threshold sharing level (0 = off)
+  int seed_m;            // sampled items of the threshold-seeding pre-pass (0 = off)
+  long long seed_stride; // item-row stride of the sample
+  long long seed_ld;     // row pitch of the sampled score matrix (floats)
+  size_t off_seed;
+  size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, off_gtau, off_gq, total;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -72,7 +78,6 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
   if (algo == CCR_ALGO_AUTO) algo = ccr_choose_algo(B, n_items, D, k);
   const int sms = device_sm_count();
   pl->algo = algo;
-  pl->C = cand_capacity(k);
   if (algo == CCR_ALGO_TCGEN05) {
     pl->n_q_tiles = (int)((B + kQTile - 1) / kQTile);
     if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
@@ -80,6 +85,22 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
     long long tiles = (n_items + kITile - 1) / kITile;
     pl->S = splits_tc(pl->n_q_tiles, tiles, sms);
     pl->halves = 2;
+    pl->C = cand_capacity(k, 128);
+    {
+      // streams of one row that run in the first wave; use half of them for the bound so a few
+      // late streams do not hold it back
+      int s_row = pl->S * pl->halves;
+      int conc_splits = (sms + pl->n_q_tiles - 1) / pl->n_q_tiles;
+      if (conc_splits > pl->S) conc_splits = pl->S;
+      int s_conc = conc_splits * pl->halves;
+      if (s_conc > 256) s_conc = 256;
+      int use = s_conc / 2 > 1 ? s_conc / 2 : 1;
+      int j = 1;
+      while ((k + j - 1) / j > use) j <<= 1;
+      if (j > k) j = k;
+      pl->share_j = (s_row > 1 && !getenv("CCR_NO_SHARE")) ? j : 0;
+      pl->share_m = (k + j - 1) / j;
+    }
   } else {
     pl->n_q_tiles = (int)((B + kSimtRows - 1) / kSimtRows);
     if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
@@ -90,6 +111,8 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
     if (s < 1) s = 1;
     pl->S = (int)s;
     pl->halves = 1;
+    pl->C = cand_capacity(k, kSimtChunk);
+    pl->share_j = 0; pl->share_m = 0;
   }
   size_t off = 0;
   pl->off_cand = off;   off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * pl->C * sizeof(u64), 256);
@@ -97,6 +120,24 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
   pl->off_ovr_hi = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u64), 256);
   pl->off_ovr_lo = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u32), 256);
   pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
+  pl->off_gtau = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(u32), 256);
+  pl->off_gq = off;     off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(u32), 256);
+  pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
+  if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !getenv("CCR_NO_SEED")) {
+    // strided sample of ~N/256 items (4096..65536), capped so the fp32 score matrix stays <= 512 MB
+    long long m = n_items / 256;
+    if (m < 4096) m = 4096;
+    if (m > 65536) m = 65536;
+    long long cap = (512LL << 20) / (4LL * pl->rows_pad);
+    if (m > cap) m = cap;
+    m = m / 256 * 256;
+    if (m >= 1024 && 4LL * k <= m) {
+      pl->seed_m = (int)m;
+      pl->seed_stride = n_items / m;
+      pl->seed_ld = m;
+      off = align_up(off + (size_t)pl->rows_pad * (size_t)m * sizeof(float), 256);
+    }
+  }
   pl->total = off;
   return true;
 }
@@ -122,6 +163,11 @@ int ccr_abi_version(void) { return CCR_ABI_VERSION; }
 const char* ccr_last_error_string(void) { return g_err; }
 
 void ccr_debug_set_status_ptr(void* device_visible_ptr) { g_status_override = device_visible_ptr; }
+
+void ccr_set_profile_events(void* start_event, void* stop_event) {
+  g_prof_start = (cudaEvent_t)start_event;
+  g_prof_stop = (cudaEvent_t)stop_event;
+}
 
 int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k) {
   (void)n_items; (void)D; (void)k;
@@ -191,15 +237,40 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.counts = (int*)(ws + pl.off_counts);
   sp.status = status;
   { const char* d = getenv("CCR_DEBUG"); sp.debug = d ? atoi(d) : 0; }
+  { const char* d = getenv("CCR_DEBUG_TAU"); sp.debug_tau = d ? (float)atof(d) : 0.f; }
+  sp.g_tau = nullptr; sp.g_q = nullptr; sp.S_row = pl.S * pl.halves; sp.share_j = pl.share_j; sp.share_m = pl.share_m;
+  sp.dense_out = nullptr; sp.ld_out = 0;
+  if (pl.share_j > 0 || pl.seed_m > 0) {
+    sp.g_tau = (u32*)(ws + pl.off_gtau);
+    sp.g_q = (u32*)(ws + pl.off_gq);
+    e = (getenv("CCR_DEBUG_KEEP_TAU") != nullptr) ? cudaSuccess : cudaMemsetAsync(ws + pl.off_gtau, 0, pl.off_seed - pl.off_gtau, st);
+    if (e != cudaSuccess) return fail(CCR_ECUDA, "memset share state: %s", cudaGetErrorString(e));
+  }
+  if (pl.seed_m > 0 && n_items > 0 && !getenv("CCR_DEBUG_KEEP_TAU")) {
+    // threshold seeding pre-pass: scores of a strided item sample -> per-row lower bound in g_tau
+    SelectParams ss = sp;
+    ss.n_items = pl.seed_m; ss.ldi = ldi * pl.seed_stride;
+    ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
+    ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld;
+    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0;
+    long long tiles = (pl.seed_m + kITile - 1) / kITile;
+    ss.S = splits_tc(pl.n_q_tiles, tiles, device_sm_count());
+    int lr0 = launch_select_tc(ss, st, device_sm_count());
+    if (lr0) return fail(CCR_ECUDA, "seed GEMM launch failed (%d)", lr0);
+    lr0 = launch_seed_tau(ss.dense_out, pl.seed_ld, pl.seed_m, (int)B, k, has_mask ? (const long long*)mask_indptr : nullptr,
+                          sp.g_tau, st);
+    if (lr0) return fail(CCR_ECUDA, "seed select launch failed: %s", cudaGetErrorString((cudaError_t)lr0));
+  }
 
   int lr = 0;
   if (n_items == 0) {
     e = cudaMemsetAsync(sp.counts, 0, (size_t)pl.rows_pad * pl.S * pl.halves * sizeof(int), st);
     if (e != cudaSuccess) return fail(CCR_ECUDA, "memset counts: %s", cudaGetErrorString(e));
-  } else if (pl.algo == CCR_ALGO_TCGEN05) {
-    lr = launch_select_tc(sp, st, device_sm_count());
   } else {
-    lr = launch_select_simt(sp, st);
+    if (g_prof_start) cudaEventRecord(g_prof_start, st);
+    if (pl.algo == CCR_ALGO_TCGEN05) lr = launch_select_tc(sp, st, device_sm_count());
+    else lr = launch_select_simt(sp, st);
+    if (g_prof_stop) cudaEventRecord(g_prof_stop, st);
   }
   if (lr) return fail(CCR_ECUDA, "select kernel launch failed (%d: %s)", lr, lr > 0 ? cudaGetErrorString((cudaError_t)lr) : "tensor map");
 

@@ -58,9 +58,18 @@ __host__ __device__ __forceinline__ u64 make_key(float s, u32 id) {
 __host__ __device__ __forceinline__ float key_score(u64 k) { return unord32((u32)(k >> 32)); }
 __host__ __device__ __forceinline__ u32 key_id(u64 k) { return 0xFFFFFFFFu - (u32)k; }
 
-// candidate-buffer capacity for a given k: room for >= k fresh inserts between prunes plus one
-// full chunk (32 columns) of slack, multiple of 64
-__host__ __device__ __forceinline__ int cand_capacity(int k) { return ((2 * k + 32 + 63) / 64) * 64; }
+// candidate-buffer capacity for a given k: room for >= k fresh inserts between prunes plus
+// `slack` columns that may be appended before the next prune opportunity (32 for the SIMT
+// kernel: one block iteration; 128 for the tensor-core kernel: one half tile), multiple of 64
+__host__ __device__ __forceinline__ int cand_capacity(int k, int slack) { return ((2 * k + slack + 63) / 64) * 64; }
+
+// smallest float strictly greater than x (x finite): "s > x"  <=>  "s >= next_up(x)"
+__device__ __forceinline__ float next_up(float x) {
+  if (!(x == x) || x == INFINITY) return x;
+  if (x == 0.f) return __uint_as_float(1u);
+  u32 b = __float_as_uint(x);
+  return __uint_as_float(x > 0.f ? b + 1u : b - 1u);
+}
 
 // ---------------------------------------------------------------------------------------
 // mask lookup: is `col` present in the sorted list cols[beg, end) ?
@@ -205,6 +214,100 @@ __device__ __forceinline__ u64 warp_prune(u64* buf, int n, int k, u32 hist_s, u3
   }
   __syncwarp();
   return pivot;
+}
+
+// ---------------------------------------------------------------------------------------
+// One-pass approximate prune (the common case).  Keys are staged in shared memory, bucketed by
+// the 8 score bits just below the bits all n keys share, and everything at or above the bucket
+// where the running count from the top reaches k is kept: between k and k + (that bucket's
+// population - 1) survivors, which is all a *threshold* needs (any value with >= k candidates at
+// or above it is a valid lower bound of the k-th best).  The same histogram gives, for free, a
+// value with >= j candidates at or above it (the stream's contribution to the shared row bound).
+// Returns false (nothing modified) when the keys do not spread over buckets (ties) or the
+// boundary bucket is too crowded; the caller then falls back to the exact radix select.
+//   out_pivot_ord : ord32 score threshold; survivors are exactly the keys with ord >= it
+//   out_kept      : survivors, compacted to buf[0, kept)
+//   out_j_ord     : ord32 value with at least j keys >= it
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool warp_prune_hist(u64* buf, int n, int k, int j, int max_keep, u32 hist_s,
+                                                u32 stage_s, u32* out_pivot_ord, int* out_kept, u32* out_j_ord) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  u32 mx = 0u, mn = 0xFFFFFFFFu;
+  for (int i = lane; i < n; i += 32) {
+    const u64 key = buf[i];
+    sm_st64(stage_s + (u32)i * 8u, key);
+    const u32 o = (u32)(key >> 32);
+    mx = o > mx ? o : mx;
+    mn = o < mn ? o : mn;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    const u32 a = __shfl_xor_sync(0xffffffffu, mx, off), b = __shfl_xor_sync(0xffffffffu, mn, off);
+    mx = a > mx ? a : mx;
+    mn = b < mn ? b : mn;
+  }
+  const u32 d = mx ^ mn;
+  if (d == 0u) return false;
+  const int hb = 31 - __clz(d);
+  const int shift = hb > 7 ? hb - 7 : 0;
+  const u32 base = mn >> shift;  // digit = (ord >> shift) - base  in [0, 255]
+#pragma unroll
+  for (int t = 0; t < 8; ++t) sm_st32(hist_s + (u32)(lane * 8 + t) * 4u, 0u);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const u32 o = (u32)(sm_ld64(stage_s + (u32)i * 8u) >> 32);
+    sm_red_inc(hist_s + ((o >> shift) - base) * 4u);
+  }
+  __syncwarp();
+  u32 c[8], lane_sum = 0;
+#pragma unroll
+  for (int t = 0; t < 8; ++t) { c[t] = sm_ld32(hist_s + (u32)(lane * 8 + t) * 4u); lane_sum += c[t]; }
+  u32 incl = lane_sum;  // keys in bins owned by lanes >= lane
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const u32 t = __shfl_down_sync(0xffffffffu, incl, off);
+    if (lane + off < 32) incl += t;
+  }
+  const u32 above = incl - lane_sum;
+  // bin where the count from the top reaches `need`, and that cumulative count
+  u32 bin_k = 0, cum_k = 0, bin_j = 0;
+  {
+    u32 run = above;
+    bool done_k = !((above < (u32)k) && ((u32)k <= incl)), done_j = !((above < (u32)j) && ((u32)j <= incl));
+#pragma unroll
+    for (int t = 7; t >= 0; --t) {
+      run += c[t];
+      if (!done_k && run >= (u32)k) { bin_k = lane * 8 + t; cum_k = run; done_k = true; }
+      if (!done_j && run >= (u32)j) { bin_j = lane * 8 + t; done_j = true; }
+    }
+  }
+  const unsigned who_k = __ballot_sync(0xffffffffu, (above < (u32)k) && ((u32)k <= incl));
+  const unsigned who_j = __ballot_sync(0xffffffffu, (above < (u32)j) && ((u32)j <= incl));
+  const int src_k = __ffs(who_k) - 1, src_j = __ffs(who_j) - 1;
+  bin_k = __shfl_sync(0xffffffffu, bin_k, src_k);
+  cum_k = __shfl_sync(0xffffffffu, cum_k, src_k);
+  bin_j = __shfl_sync(0xffffffffu, bin_j, src_j);
+  if ((int)cum_k > max_keep) return false;
+  u32 pivot_ord = (base + bin_k) << shift;
+  if (pivot_ord < 0x00800000u) pivot_ord = 0x00800000u;  // never below ord32(-FLT_MAX): stays a finite float
+  // compaction stage -> buf (stable)
+  int wbase = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    const u64 key = (i < n) ? sm_ld64(stage_s + (u32)i * 8u) : 0ull;
+    const bool keep = (i < n) && ((u32)(key >> 32) >= pivot_ord);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[wbase + __popc(m & ((1u << lane) - 1u))] = key;
+    wbase += __popc(m);
+  }
+  __syncwarp();
+  *out_pivot_ord = pivot_ord;
+  *out_kept = wbase;
+  u32 j_ord = (base + bin_j) << shift;
+  if (j_ord < 0x00800000u) j_ord = 0x00800000u;
+  *out_j_ord = j_ord;
+  return true;
 }
 
 // Append one candidate (noinline: keeps the unrolled per-column hit tests small).

@@ -23,7 +23,21 @@ struct SelectParams {
   const int* mask_cols;
   u64* cand;
   int* counts;
+  // cross-stream threshold sharing (tensor-core kernel; null/0 = off).  A "stream" is one
+  // (row, split, half) candidate list.  Every stream publishes the score of its share_j-th best
+  // candidate (g_q, monotone); the share_m-th largest published value over the row's streams is a
+  // lower bound of the row's global k-th best (share_m * share_j >= k distinct unmasked items
+  // score at least that much) and is max-reduced into g_tau[row].
+  u32* g_tau;   // [rows_pad]            ord32(score), 0 = nothing known
+  u32* g_q;     // [rows_pad][S_row]     ord32(score), 0 = not published
+  int S_row;    // streams per row
+  int share_j;
+  int share_m;
   DeviceStatus* status;
+  // store mode (threshold seeding pre-pass): write fp32 scores instead of selecting
+  float* dense_out;      // [rows_pad][ld_out], null in select mode
+  long long ld_out;
+  float debug_tau;  // CCR_DEBUG & 16: fixed threshold, no prune (cnt wraps); & 32: also no store
   int debug;  // CCR_DEBUG bits (env, diagnostics only): 1 = skip selection, keep pipeline
 };
 
@@ -64,6 +78,8 @@ struct OverrideParams {
 // launchers (return cudaError_t as int)
 int launch_select_simt(const SelectParams& p, cudaStream_t st);
 int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms);
+int launch_seed_tau(const float* scores, long long ld, int m, int B, int k, const long long* mask_indptr,
+                    u32* g_tau, cudaStream_t st);
 int launch_overrides(const OverrideParams& p, cudaStream_t st);
 int launch_finalize(const FinalizeParams& p, cudaStream_t st);
 int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,

@@ -14,6 +14,7 @@
 // Persistent: grid = #SMs, each CTA walks units (query tile, item split) round-robin with the
 // query tile varying fastest so CTAs running concurrently share item tiles through L2.
 #include <cuda.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "ccr_params.cuh"
@@ -25,8 +26,10 @@ constexpr int kBytesA = kQTile * kKBlock * 2;   // 16384
 constexpr int kBytesB = kITile * kKBlock * 2;   // 32768
 constexpr int kStageBytes = kBytesA + kBytesB;  // 49152
 constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, one per column half
-constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int kStageKeys = 256;                 // candidate buffers up to this size are pruned in smem
+constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA (the
+                                                // scheduler favours high warp ids: keep the feeders there)
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kStageKeys = 384;                 // candidate buffers up to this size are pruned in smem
 constexpr int kTmemCols = 512;
 constexpr unsigned long long kWaitLimitNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
 
@@ -56,6 +59,11 @@ __device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(u64* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// relaxed arrive: the TMEM reads it publishes are already complete (tcgen05.wait::ld); a release
+// arrive would additionally wait for this thread's outstanding candidate stores to global memory
+__device__ __forceinline__ void mbar_arrive_relaxed(u64* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(u64* bar, u32 parity) {
   u32 ok;
@@ -132,14 +140,19 @@ __device__ __forceinline__ u64 make_sw128_desc(u32 saddr) {
 constexpr u32 kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kITile >> 3) << 17) | ((u32)(kQTile >> 4) << 24);
 
 // ---------------------------------------------------------------------------------------
-// per-thread selection state and the per-chunk filter (32 columns of one query row)
+// per-thread selection state, the per-chunk filter (32 columns of one query row) and the
+// deferred prune
 // ---------------------------------------------------------------------------------------
 struct SelState {
   u64* buf;        // this (row, split, half)'s candidate buffer
-  int cnt;
-  float tau_f;     // score of the current k-th best (or -inf / +inf for padding rows)
-  u64 tau_key;
+  int cnt;         // keys currently in buf
+  float tau_f;     // pass iff score >= tau_f: max(next_up(local k-th best), shared row bound),
+                   // -inf before the first prune, +inf for padding rows
   long long mbeg, mend;  // the row's slice of the mask CSR
+  u64 sig;         // 64-bit signature of the row's masked columns (bit col & 63)
+  int row;         // global query row
+  int stream;      // index of this stream among the row's streams
+  unsigned n_slow, n_prune;  // debug counters (CCR_DEBUG & 4)
 };
 
 __device__ __forceinline__ float max8(const u32 (&v)[32], int g) {
@@ -149,44 +162,169 @@ __device__ __forceinline__ float max8(const u32 (&v)[32], int g) {
   return fmaxf(fmaxf(a, b), c);
 }
 
-__device__ __forceinline__ void select_chunk(const u32 (&v)[32], long long col0, SelState& st, const SelectParams& p,
-                                             int k, int C, u32 hist_s, u32 stage_s) {
-  const int lane = threadIdx.x & 31;
+// exact membership test for a column whose signature bit is set (rare)
+static __device__ __noinline__ bool masked_slow(const int* mask_cols, long long mbeg, long long mend, int col) {
+  return mask_contains(mask_cols, mbeg, mend, col);
+}
+
+// Branch-free conditional append: if (s >= tau) { buf[cnt] = make_key(s, ~nlo); ++cnt; }
+// written as predicated PTX so that a group of 8 columns costs a fixed, short, straight-line
+// sequence whatever the number of hits.
+template <int J>
+__device__ __forceinline__ void append_if_ge(u32 sbits, float tau, u32 nlo0, u64* buf, int& cnt) {
+  if (__uint_as_float(sbits) >= tau) {
+    const u32 hi = sbits ^ ((u32)((int)sbits >> 31) | 0x80000000u);
+    buf[cnt] = ((u64)hi << 32) | (u64)(nlo0 - (u32)J);
+    cnt += 1;
+  }
+}
+
+// Append every score >= tau_f of this 32-column chunk to the row's buffer.  Warp-uniform votes
+// decide whether a group of 8 columns is looked at; inside a group the appends are predicated
+// (no branches, no calls, no key compares): the strict local threshold already encodes the
+// lowest-id tie rule because a stream sees its items in ascending id order.
+template <bool kMask>
+__device__ __forceinline__ void filter_chunk(const u32 (&v)[32], u32 col0, SelState& st, const SelectParams& p) {
   if (p.debug & 1) return;
   float m8[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) m8[g] = max8(v, g);
   const float m = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
   if (!__any_sync(0xffffffffu, m >= st.tau_f)) return;
-  // slow path: some row of this warp has a candidate in these 32 columns
+  st.n_slow++;
+  const u32 nlo0 = 0xFFFFFFFFu - col0;  // low key word of column col0; column col0+j -> nlo0 - j
+#define CCR_APPEND(J)                                                                            \
+  if (kMask) {                                                                                   \
+    u32 sb = v[J];                                                                               \
+    const u32 col = col0 + (u32)(J);                                                             \
+    if (__uint_as_float(sb) >= st.tau_f && ((st.sig >> (col & 63u)) & 1ull)) {                   \
+      if (masked_slow(p.mask_cols, st.mbeg, st.mend, (int)col)) sb = 0x7fc00000u;                \
+    }                                                                                            \
+    append_if_ge<J>(sb, st.tau_f, nlo0, st.buf, st.cnt);                                         \
+  } else {                                                                                       \
+    append_if_ge<J>(v[J], st.tau_f, nlo0, st.buf, st.cnt);                                       \
+  }
+#define CCR_GROUP(G)                                                                             \
+  if (__any_sync(0xffffffffu, m8[G] >= st.tau_f)) {                                              \
+    CCR_APPEND(G * 8 + 0) CCR_APPEND(G * 8 + 1) CCR_APPEND(G * 8 + 2) CCR_APPEND(G * 8 + 3)      \
+    CCR_APPEND(G * 8 + 4) CCR_APPEND(G * 8 + 5) CCR_APPEND(G * 8 + 6) CCR_APPEND(G * 8 + 7)      \
+  }
+  CCR_GROUP(0) CCR_GROUP(1) CCR_GROUP(2) CCR_GROUP(3)
+  if (p.debug & 16) st.cnt &= 127;
+#undef CCR_GROUP
+#undef CCR_APPEND
+  asm volatile("" ::: "memory");  // appended keys are read back by the prune
+}
+
+// columns at or beyond n_items (zero-filled by TMA) must never be selected
+__device__ __forceinline__ void clamp_ragged(u32 (&v)[32], long long col0, long long n_items) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (m8[g] >= st.tau_f) {
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        const float s = __uint_as_float(v[g * 8 + jj]);
-        if (s >= st.tau_f) {
-          const long long col = col0 + g * 8 + jj;
-          if (col < p.n_items)
-            st.cnt = cand_insert(s, (u32)col, st.cnt, st.tau_key, st.buf, p.mask_cols, st.mbeg, st.mend);
-        }
-      }
+  for (int j = 0; j < 32; ++j)
+    if (col0 + j >= n_items) v[j] = 0x7fc00000u;  // NaN: ignored by fmaxf, fails every >= test
+}
+
+// Everything below the per-chunk filter is deliberately kept OUT of line (one copy each): the
+// epilogue's common path must stay resident in the instruction caches.
+struct ShareArgs {
+  u32* g_tau;
+  u32* g_q;
+  int S_row, share_j, share_m;
+};
+
+// m-th largest of the row's published stream values (0 = unpublished) -- the shared lower bound.
+static __device__ __noinline__ u32 sketch_bound(const u32* gq, int S_row, int m, int own_stream, u32 own_val,
+                                                u32 hist_s, u32 stage_s) {
+  const int lane = threadIdx.x & 31;
+  if (S_row <= 32) {
+    u32 v = 0u;
+    if (lane < S_row) v = (lane == own_stream) ? own_val : __ldcg(gq + lane);
+    int gt = 0, ge = 0;
+#pragma unroll 4
+    for (int i = 0; i < 32; ++i) {
+      const u32 o = __shfl_sync(0xffffffffu, v, i);
+      gt += (o > v);
+      ge += (o >= v);
+    }
+    const unsigned who = __ballot_sync(0xffffffffu, gt < m && m <= ge);
+    return who ? __shfl_sync(0xffffffffu, v, __ffs(who) - 1) : 0u;
+  }
+  const int ns = S_row < kStageKeys ? S_row : kStageKeys;
+  for (int i = lane; i < ns; i += 32) {
+    const u32 qv = (i == own_stream) ? own_val : __ldcg(gq + i);
+    sm_st64(stage_s + (u32)i * 8u, ((u64)qv << 32) | (u64)(u32)(ns - i));
+  }
+  __syncwarp();
+  return (u32)(warp_select_kth(SharedKeys{stage_s}, ns, m, hist_s) >> 32);
+}
+
+static __device__ __noinline__ u64 exact_prune(u64* b, int n, int k, int j, bool staged, u32 hist_s, u32 stage_s,
+                                               u32* j_ord) {
+  const u64 pivot = warp_prune(b, n, k, hist_s, staged ? stage_s : 0u);
+  if (j > 0) {
+    u64 kj;
+    if (staged) kj = warp_select_kth(SharedKeys{stage_s}, n, j, hist_s);
+    else kj = warp_select_kth(GlobalKeys{b}, k, j, hist_s);
+    *j_ord = (u32)(kj >> 32);
+  }
+  return pivot;
+}
+
+// Prune one stream's buffer (all 32 lanes cooperate), publish its share_j-th best, refresh the
+// row's shared bound.  Returns (kept << 32) | float bits of the stream's new threshold.
+static __device__ __noinline__ u64 prune_stream(u64* b, int n, int k, int C, int row_s, int stream_s, ShareArgs sh,
+                                                u32 hist_s, u32 stage_s, int debug) {
+  const int lane = threadIdx.x & 31;
+  const bool staged = C <= kStageKeys;
+  const int jj = sh.share_j > 0 ? sh.share_j : k;
+  float new_tau;
+  int kept = k;
+  u32 j_ord = 0u, pivot_ord = 0u;
+  // fast path: one histogram pass; leaves between k and (k + C-128)/2 survivors
+  const bool fast = staged && !(debug & 64) &&
+                    warp_prune_hist(b, n, k, jj, (k + C - 128) / 2, hist_s, stage_s, &pivot_ord, &kept, &j_ord);
+  if (fast) {
+    new_tau = unord32(pivot_ord);  // ">=": every key at or above the pivot bucket was kept
+  } else {
+    const u64 pivot = exact_prune(b, n, k, sh.share_j, staged, hist_s, stage_s, &j_ord);
+    new_tau = next_up(key_score(pivot));
+    kept = k;
+  }
+  if (sh.share_j > 0) {
+    u32* gq = sh.g_q + (long long)row_s * sh.S_row;
+    if (lane == 0) gq[stream_s] = j_ord;
+    const u32 bound = sketch_bound(gq, sh.S_row, sh.share_m, stream_s, j_ord, hist_s, stage_s);
+    if (bound != 0u) {
+      if (lane == 0) atomicMax(sh.g_tau + row_s, bound);  // no return value needed: RED
+      if (bound > ord32(new_tau)) new_tau = unord32(bound);
     }
   }
-  unsigned need = __ballot_sync(0xffffffffu, st.cnt > C - 32);
+  return ((u64)(u32)kept << 32) | (u64)__float_as_uint(new_tau);
+}
+
+// Prune every stream of this warp whose buffer could overflow during the next half tile.  Runs
+// after the accumulator has been handed back, i.e. off the MMA critical path.
+__device__ __forceinline__ void prune_pending(SelState& st, const ShareArgs& sh, int k, int C, u32 hist_s,
+                                              u32 stage_s, int debug) {
+  const int lane = threadIdx.x & 31;
+  unsigned need = __ballot_sync(0xffffffffu, st.cnt > C - 128);
   while (need) {
+    st.n_prune++;
     const int src = __ffs(need) - 1;
     need &= need - 1;
     u64* b = reinterpret_cast<u64*>(__shfl_sync(0xffffffffu, (u64)(uintptr_t)st.buf, src));
     const int n = __shfl_sync(0xffffffffu, st.cnt, src);
-    const u64 pivot = warp_prune(b, n, k, hist_s, stage_s);
-    if (lane == src) { st.cnt = k; st.tau_key = pivot; st.tau_f = key_score(pivot); }
+    const int row_s = __shfl_sync(0xffffffffu, st.row, src);
+    const int stream_s = __shfl_sync(0xffffffffu, st.stream, src);
+    const u64 r = prune_stream(b, n, k, C, row_s, stream_s, sh, hist_s, stage_s, debug);
+    if (lane == src) { st.cnt = (int)(r >> 32); st.tau_f = __uint_as_float((u32)r); }
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------
+// kMode: 0 select (no mask), 1 select (mask CSR), 2 store fp32 scores (seeding pre-pass)
+template <int kMode>
 __global__ void __launch_bounds__(kTcThreads, 1)
 select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_items,
                  SelectParams p) {
@@ -207,7 +345,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_items) : "memory");
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"((u32)kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -217,7 +355,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_after();
   const u32 tmem_base = sh->tmem_base;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
@@ -236,7 +374,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
@@ -267,64 +405,197 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
+  } else if (kMode == 2) {
+    // ===== store epilogue: thread == query row, writes its 128 columns of the tile as fp32 =====
+    const int quad = warp & 3, half = warp >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0; u32 acc_phase = 0;
+    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
+      const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
+      float* orow = p.dense_out + (long long)(qt * kQTile + row_in_tile) * p.ld_out;
+      for (long long t = t0; t < t1; ++t) {
+        mbar_wait(&sh->tmem_full[acc], acc_phase, p.status, 400 + acc);
+        tc_fence_after();
+        const u32 taddr0 = tmem_base + ((u32)(quad * 32) << 16) + (u32)(acc * kITile + half * 128);
+        const long long col0 = t * kITile + half * 128;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          u32 v[32];
+          tmem_ld_32x32b_x32(taddr0 + (u32)(32 * c), v);
+          tmem_ld_wait();
+          float4* o4 = reinterpret_cast<float4*>(orow + col0 + 32 * c);  // ld_out % 256 == 0: in bounds
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
   } else {
+    constexpr bool kMask = (kMode == 1);
     // ===== epilogue / selection: 8 warps; thread == (query row, 128-column half of the tile) =====
-    const int ew = warp - 2;
+    const int ew = warp;
     const int quad = warp & 3;   // TMEM lane quadrant this warp may access
     const int half = ew >> 2;    // 0: tile columns [0,128), 1: [128,256)
     const int row_in_tile = quad * 32 + lane;
     const u32 hist_s = smem_addr(sh->hist[ew]);
+    const u32 stage_s = smem_addr(sh->stage[ew]);
     const int k = p.k, C = p.C;
-    const u32 stage_s = (C <= kStageKeys) ? smem_addr(sh->stage[ew]) : 0u;
+    ShareArgs sa;
+    sa.g_tau = p.g_tau; sa.g_q = p.g_q; sa.S_row = p.S_row; sa.share_j = p.share_j; sa.share_m = p.share_m;
     int acc = 0; u32 acc_phase = 0;
     for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
       const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
       const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
       const int row = qt * kQTile + row_in_tile;
       const bool valid_row = row < p.B;
+      unsigned long long t_start = 0;
+      if (p.debug & (4 | 128)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
       SelState st;
+      st.n_slow = st.n_prune = 0;
       st.buf = p.cand + (((long long)row * p.S + u) * 2 + half) * C;
       st.cnt = 0;
-      st.tau_f = valid_row ? -INFINITY : INFINITY;
-      st.tau_key = 0ull;
-      st.mbeg = 0; st.mend = 0;
-      if (p.mask_indptr && valid_row) { st.mbeg = p.mask_indptr[row]; st.mend = p.mask_indptr[row + 1]; }
+      st.tau_f = (valid_row && !(p.debug & 2)) ? -INFINITY : INFINITY;  // debug 2: reject everything
+      if ((p.debug & 16) && valid_row) st.tau_f = p.debug_tau;
+      st.mbeg = 0; st.mend = 0; st.sig = 0ull;
+      st.row = row; st.stream = u * 2 + half;
+      if (kMask && valid_row) {
+        st.mbeg = p.mask_indptr[row]; st.mend = p.mask_indptr[row + 1];
+        for (long long e = st.mbeg; e < st.mend; ++e) st.sig |= 1ull << ((u32)__ldg(p.mask_cols + e) & 63u);
+      }
 
       for (long long t = t0; t < t1; ++t) {
+        u32 gt = 0u;
+        if (p.g_tau && valid_row && !(p.debug & 8)) gt = __ldcg(p.g_tau + row);  // issued before the wait
         mbar_wait(&sh->tmem_full[acc], acc_phase, p.status, 400 + acc);
         tc_fence_after();
+        if (gt > ord32(st.tau_f) && !(p.debug & 16)) st.tau_f = unord32(gt);
         const u32 taddr0 = tmem_base + ((u32)(quad * 32) << 16) + (u32)(acc * kITile + half * 128);
         const long long col0 = t * kITile + half * 128;
-        u32 va[32], vb[32];
-        tmem_ld_32x32b_x32(taddr0, va);
+        const bool ragged = col0 + 128 > p.n_items;
+        u32 v[32], w[32];
+        tmem_ld_32x32b_x32(taddr0, v);
         tmem_ld_wait();
-        tmem_ld_32x32b_x32(taddr0 + 32, vb);
-        select_chunk(va, col0, st, p, k, C, hist_s, stage_s);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(taddr0 + 64, va);
-        select_chunk(vb, col0 + 32, st, p, k, C, hist_s, stage_s);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(taddr0 + 96, vb);
-        select_chunk(va, col0 + 64, st, p, k, C, hist_s, stage_s);
-        tmem_ld_wait();
-        // every column of this half is in registers: hand the accumulator back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->tmem_empty[acc]);
-        select_chunk(vb, col0 + 96, st, p, k, C, hist_s, stage_s);
+        // one filter call site: chunk c is filtered from v while chunk c+1 streams into w
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          if (c < 3) {
+            tmem_ld_32x32b_x32(taddr0 + (u32)(32 * (c + 1)), w);
+          } else {
+            // every column of this half is in registers: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+          }
+          if (ragged) clamp_ragged(v, col0 + 32 * c, p.n_items);
+          filter_chunk<kMask>(v, (u32)col0 + (u32)(32 * c), st, p);
+          if (c < 3) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = w[j];
+          }
+        }
+        if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug);
+        if ((p.debug & 128) && blockIdx.x == 0 && ew == 0 && lane == 0) {
+          const long long ti = t - t0 + 1;
+          if ((ti & (ti - 1)) == 0 || t + 1 == t1) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            printf("[ccr tl] unit %d tile %lld us %llu slow %u prunes %u cnt %d tau %f\n", unit, ti,
+                   (now - t_start) / 1000ull, st.n_slow, st.n_prune, st.cnt, st.tau_f);
+          }
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
       p.counts[((long long)row * p.S + u) * 2 + half] = st.cnt;
+      if ((p.debug & 4) && blockIdx.x < 2) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+        if (lane == 0)
+          printf("[ccr stats] cta %d unit %d warp %d tiles %lld slow %u prunes %u cnt(lane0) %d tau %f us %llu\n",
+                 blockIdx.x, unit, ew, t1 - t0, st.n_slow, st.n_prune, st.cnt, st.tau_f,
+                 (t_end - t_start) / 1000ull);
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)kTmemCols)
                  : "memory");
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Threshold seeding: per row, the (k + h)-th largest of the m sampled scores (h = number of
+// mask entries of the row, so that even if every masked item were in the sample at least k
+// unmasked sampled items score that much) is a valid lower bound of the row's k-th best.
+// One block per row, MSB-first radix select over ord32(score).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seed_tau_kernel(const float* __restrict__ scores, long long ld, int m, int B,
+                                                       int k, const long long* __restrict__ mask_indptr,
+                                                       u32* __restrict__ g_tau) {
+  __shared__ u32 hist[256];
+  __shared__ u32 s_d, s_need;
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+  long long h = mask_indptr ? (mask_indptr[row + 1] - mask_indptr[row]) : 0;
+  long long kth = (long long)k + h;
+  if (kth > m) return;  // no bound for this row
+  const float* r = scores + (long long)row * ld;
+  u32 prefix = 0, pmask = 0;
+  int need = (int)kth;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < m; i += 256) {
+      const u32 o = ord32(r[i]);
+      if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      u32 c[8], lane_sum = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) { c[t] = hist[lane * 8 + t]; lane_sum += c[t]; }
+      u32 incl = lane_sum;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const u32 t = __shfl_down_sync(0xffffffffu, incl, off);
+        if (lane + off < 32) incl += t;
+      }
+      const u32 above = incl - lane_sum;
+      if (above < (u32)need && (u32)need <= incl) {
+        u32 run = above;
+        bool done = false;
+#pragma unroll
+        for (int t = 7; t >= 0; --t) {
+          if (!done) {
+            if (run + c[t] >= (u32)need) { s_d = lane * 8 + t; s_need = need - run; done = true; }
+            else run += c[t];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= s_d << shift;
+    pmask |= 0xFFu << shift;
+    need = (int)s_need;
+    __syncthreads();
+  }
+  if (tid == 0 && prefix >= 0x00800000u && prefix <= 0xFF7FFFFFu) g_tau[row] = prefix;  // finite scores only
+}
+
+int launch_seed_tau(const float* scores, long long ld, int m, int B, int k, const long long* mask_indptr, u32* g_tau,
+                    cudaStream_t st) {
+  if (B <= 0) return 0;
+  seed_tau_kernel<<<B, 256, 0, st>>>(scores, ld, m, B, k, mask_indptr, g_tau);
+  return (int)cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------
@@ -366,14 +637,14 @@ int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms) {
   if (r) return r;
   r = make_tmap(&ti, p.items, p.n_items, p.D, p.ldi, kITile);
   if (r) return r;
-  cudaError_t e = cudaFuncSetAttribute(select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kTcSmemBytes);
+  auto kern = p.dense_out ? select_tc_kernel<2> : (p.mask_cols ? select_tc_kernel<1> : select_tc_kernel<0>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
   if (e != cudaSuccess) return (int)e;
   int n_units = p.n_q_tiles * p.S;
   int grid = n_units < num_sms ? n_units : num_sms;
   if (const char* g = getenv("CCR_DEBUG_GRID")) { int v = atoi(g); if (v > 0 && v < grid) grid = v; }
   if (grid < 1) grid = 1;
-  select_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tq, ti, p);
+  kern<<<grid, kTcThreads, kTcSmemBytes, st>>>(tq, ti, p);
   return (int)cudaGetLastError();
 }
 

@@ -134,6 +134,15 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
 /* Which kernel ccr_score_topk_bf16 picks under CCR_ALGO_AUTO: CCR_ALGO_SIMT or CCR_ALGO_TCGEN05. */
 int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k);
 
+/*
+ * Measurement hook: when both are non-NULL (cudaEvent_t passed as void*), every later
+ * ccr_score_topk_bf16 call on this host thread records `start_event` immediately before and
+ * `stop_event` immediately after its dominant kernel (the fused score+select kernel) on the
+ * call's stream, so a benchmark can time that kernel alone without a profiler.  Pass NULLs to
+ * switch it off.
+ */
+void ccr_set_profile_events(void* start_event, void* stop_event);
+
 /* Launch geometry of the last-configured plan, for benchmarks / DESIGN.md bookkeeping:
  * fills n_q_tiles, n_splits, cand_capacity, n_launches.  Returns 0 or CCR_E*. */
 int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* info4);
