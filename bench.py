@@ -226,11 +226,11 @@ def run_ours(args):
     def step_resident():
         if world > 1:
             d, i = index._local_topk(q_dev, k, mask_local)
-            gs = torch.empty((world,) + tuple(d.shape), dtype=d.dtype, device=dev)
-            gi = torch.empty((world,) + tuple(i.shape), dtype=i.dtype, device=dev)
+            gs = torch.empty((world * B, k), dtype=d.dtype, device=dev)
+            gi = torch.empty((world * B, k), dtype=i.dtype, device=dev)
             dist.all_gather_into_tensor(gs, d)
             dist.all_gather_into_tensor(gi, i)
-            return engine.merge_topk(gs, gi, k)[:2]
+            return engine.merge_topk(gs.view(world, B, k), gi.view(world, B, k), k)[:2]
         return table.search(q_dev, k, mask=mask_local, encoded=True)
 
     def step_e2e():

@@ -60,8 +60,9 @@ class ShardedIndex:
         d, i = self._local_topk(q, k, local_mask)
         if self.world == 1:
             return self._merge(d.unsqueeze(0), i.unsqueeze(0), k)
-        gs = torch.empty((self.world,) + tuple(d.shape), dtype=d.dtype, device=d.device)
-        gi = torch.empty((self.world,) + tuple(i.shape), dtype=i.dtype, device=i.device)
+        B = d.shape[0]
+        gs = torch.empty((self.world * B, k), dtype=d.dtype, device=d.device)   # rank-major concatenation
+        gi = torch.empty((self.world * B, k), dtype=i.dtype, device=i.device)
         dist.all_gather_into_tensor(gs, d.contiguous(), group=self.group)
         dist.all_gather_into_tensor(gi, i.contiguous(), group=self.group)
-        return self._merge(gs, gi, k)
+        return self._merge(gs.view(self.world, B, k), gi.view(self.world, B, k), k)

@@ -1,0 +1,145 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host-side logic
+(lazy score algebra, fused-plan recognition, mask helpers, sharding arithmetic) behaves like the
+reference.  No kernel is launched here."""
+import ctypes
+import operator
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+import torch
+
+import cases
+import _ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ccr_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "ccr_b200.h")).read()
+    declared = set(re.findall(r"\b(ccr_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert _lib.lib().ccr_abi_version() == 1
+
+
+def test_planning_entry_points_work_without_gpu():
+    from ccr_b200 import _lib
+
+    L = _lib.lib()
+    assert L.ccr_score_topk_workspace_bytes(4096, 8841823, 768, 100, 0, 0) > 0
+    assert L.ccr_score_topk_workspace_bytes(0, 100, 64, 5, 0, 0) > 0        # B == 0 must not crash
+    assert L.ccr_score_topk_workspace_bytes(4, 100, 63, 5, 0, 0) == 0       # D % 8 != 0 -> invalid
+    assert L.ccr_score_topk_workspace_bytes(4, 100, 64, 5000, 0, 0) == 0    # k > CCR_MAX_K
+    assert L.ccr_choose_algo(4, 1000, 768, 10) == _lib.ALGO_SIMT
+    assert L.ccr_choose_algo(512, 1000, 768, 10) == _lib.ALGO_TCGEN05
+    info = _lib.plan_info(4096, 8841823, 768, 100)
+    assert info["n_q_tiles"] == 32 and info["cand_capacity"] == 384 and info["n_splits"] >= 5
+
+
+def test_product_refuses_cpu_tensors():
+    import ccr_b200
+
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ccr_b200.score_topk(torch.zeros(2, 8, dtype=torch.bfloat16), torch.zeros(4, 8, dtype=torch.bfloat16), 1)
+    with pytest.raises(RuntimeError):
+        ccr_b200.EmbeddingTable(10, 8, device="cpu")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "crowd-coachable-recommendations_b200", "ccr_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("al_oracle_agent", ""), fn
+
+
+def test_shard_bounds_partition():
+    from ccr_b200 import shard_bounds
+
+    for n, g in [(10, 3), (8841823, 8), (5, 8), (0, 2), (100_000_000, 8)]:
+        parts = [shard_bounds(n, g, r) for r in range(g)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(hi - lo <= -(-n // g) for lo, hi in parts)
+
+
+def test_fused_plan_recognition():
+    import ccr_b200 as C
+
+    c = cases.rime_case("mask_prior_k10")
+    S = C.LazyDenseMatrix(c["U"]) @ C.LazyDenseMatrix(c["V"]).T
+    plan = C.fused_plan(S)
+    assert plan is not None and plan.sparse is None and plan.shape == (17, 257)
+    S2 = S + c["prior"] - c["prior"] * 0.5
+    plan2 = C.fused_plan(S2)
+    assert plan2 is not None
+    np.testing.assert_allclose(plan2.sparse.toarray(), (c["prior"] * 0.5).toarray())
+    assert C.fused_plan(S.exp()) is None
+    assert C.fused_plan(S * 2.0) is None
+    assert C.fused_plan(C.LazyDenseMatrix(np.zeros((3, 4)))) is None
+    # row slicing keeps the right factor object (so its device table is uploaded once)
+    assert S2[0:4].children[0].children[0].right is S.right
+
+
+@pytest.mark.skipif(not _ref_loader.reference_available(), reason="needs /root/reference")
+def test_lazy_algebra_matches_reference_classes():
+    import ccr_b200 as C
+
+    ru = _ref_loader.load_rime_lite_util()
+    c = cases.rime_case("mask_prior_k10")
+    ours = C.LazyDenseMatrix(c["U"]) @ C.LazyDenseMatrix(c["V"]).T + c["prior"]
+    ref = ru.LazyDenseMatrix(c["U"]) @ ru.LazyDenseMatrix(c["V"]).T + c["prior"]
+    assert ours.shape == ref.shape and len(ours) == len(ref) and ours.size == ref.size
+    assert ours.batch_size == ref.batch_size
+    for key in (slice(0, 5), slice(3, 17), [1, 4, 9]):
+        a, b = ours[key], ref[key]
+        assert a.shape == b.shape
+        torch.testing.assert_close(a.as_tensor("cpu"), b.as_tensor("cpu"))
+    torch.testing.assert_close(ours.T.as_tensor("cpu"), ref.T.as_tensor("cpu"))
+    parts_o = [ours[i:min(17, i + 4)] for i in range(0, 17, 4)]
+    parts_r = [ref[i:min(17, i + 4)] for i in range(0, 17, 4)]
+    torch.testing.assert_close(ours.collate_fn(parts_o).as_tensor("cpu"), ref.collate_fn(parts_r).as_tensor("cpu"))
+    assert float(C.score_op(ours, "max")) == float(ru.score_op(ref, "max"))
+    e_o, e_r = (ours * 0.5).sigmoid(), (ref * 0.5).sigmoid()
+    torch.testing.assert_close(e_o.as_tensor("cpu"), e_r.as_tensor("cpu"))
+    s_o, s_r = C.auto_cast_lazy_score(c["prior"]), ru.auto_cast_lazy_score(c["prior"])
+    torch.testing.assert_close(s_o[2:6].as_tensor("cpu"), s_r[2:6].as_tensor("cpu"))
+    assert type(s_o.collate_fn([s_o[i] for i in range(3)])).__name__ == "LazySparseMatrix"
+
+
+def test_mask_helpers_on_cpu_arrays():
+    """SparseMask canonicalisation / row slicing / column sharding arithmetic (host arrays only)."""
+    from ccr_b200 import engine
+
+    def host(m):  # build without touching a device
+        return m
+
+    class _M(engine.SparseMask):
+        def __init__(self, indptr, cols, vals, n_cols, mode, device=None):
+            self.n_rows = len(indptr) - 1
+            self.n_cols = int(n_cols)
+            self.mode = mode
+            self.nnz = int(indptr[-1])
+            self.host = (np.asarray(indptr, np.int64), np.asarray(cols, np.int32), np.asarray(vals, np.float64))
+            self.device = None
+
+    engine_SparseMask = engine.SparseMask
+    try:
+        engine.SparseMask = _M
+        m = _M([0, 2, 2, 5], [1, 7, 0, 4, 9], [-1.0, -2.0, 3.0, 4.0, 5.0], 10, engine.MASK_ADD)
+        r = engine_SparseMask.rows(m, 1, 3)
+        assert r.host[0].tolist() == [0, 0, 3] and r.host[1].tolist() == [0, 4, 9]
+        s = engine_SparseMask.column_shard(m, 4, 10)
+        assert s.n_cols == 6 and s.host[0].tolist() == [0, 1, 1, 3]
+        assert s.host[1].tolist() == [3, 0, 5] and s.host[2].tolist() == [-2.0, 4.0, 5.0]
+        e = engine_SparseMask.column_shard(m, 2, 4)
+        assert e.nnz == 0 and e.host[0].tolist() == [0, 0, 0, 0]
+    finally:
+        engine.SparseMask = engine_SparseMask
