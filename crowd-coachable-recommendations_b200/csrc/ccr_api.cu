@@ -49,6 +49,7 @@ struct Plan {
   long long seed_stride; // item-row stride of the sample
   long long seed_ld;     // row pitch of the sampled score matrix (floats)
   size_t off_seed;
+  size_t off_progress;
   size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, off_gtau, off_gq, total;
 };
 
@@ -122,6 +123,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
   pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
   pl->off_gtau = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(u32), 256);
   pl->off_gq = off;     off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(u32), 256);
+  pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
   pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
   if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !getenv("CCR_NO_SEED")) {
     // strided sample of ~N/256 items (4096..65536), capped so the fp32 score matrix stays <= 512 MB
@@ -240,6 +242,12 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   { const char* d = getenv("CCR_DEBUG_TAU"); sp.debug_tau = d ? (float)atof(d) : 0.f; }
   sp.g_tau = nullptr; sp.g_q = nullptr; sp.S_row = pl.S * pl.halves; sp.share_j = pl.share_j; sp.share_m = pl.share_m;
   sp.dense_out = nullptr; sp.ld_out = 0;
+  sp.progress = nullptr;
+  if (pl.algo == CCR_ALGO_TCGEN05 && getenv("CCR_THROTTLE")) {  // opt-in: see DESIGN.md §8
+    sp.progress = (int*)(ws + pl.off_progress);
+    e = cudaMemsetAsync(sp.progress, 0, (size_t)pl.n_q_tiles * pl.S * sizeof(int), st);
+    if (e != cudaSuccess) return fail(CCR_ECUDA, "memset progress: %s", cudaGetErrorString(e));
+  }
   if (pl.share_j > 0 || pl.seed_m > 0) {
     sp.g_tau = (u32*)(ws + pl.off_gtau);
     sp.g_q = (u32*)(ws + pl.off_gq);
@@ -252,7 +260,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     ss.n_items = pl.seed_m; ss.ldi = ldi * pl.seed_stride;
     ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
     ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld;
-    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0;
+    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr;
     long long tiles = (pl.seed_m + kITile - 1) / kITile;
     ss.S = splits_tc(pl.n_q_tiles, tiles, device_sm_count());
     int lr0 = launch_select_tc(ss, st, device_sm_count());

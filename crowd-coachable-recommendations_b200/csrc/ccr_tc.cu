@@ -29,6 +29,7 @@ constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, one
 constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA (the
                                                 // scheduler favours high warp ids: keep the feeders there)
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kLeadTiles = 16;                  // max lead (item tiles) over the slowest CTA on the same split
 constexpr int kStageKeys = 384;                 // candidate buffers up to this size are pruned in smem
 constexpr int kTmemCols = 512;
 constexpr unsigned long long kWaitLimitNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
@@ -362,7 +363,34 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
         const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
         const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
+        // peers: units of the same item split scheduled in the same persistent iteration
+        int peer_lo = u * p.n_q_tiles, peer_hi = peer_lo + p.n_q_tiles;
+        {
+          const int it_lo = (unit / (int)gridDim.x) * (int)gridDim.x, it_hi = it_lo + (int)gridDim.x;
+          peer_lo = peer_lo > it_lo ? peer_lo : it_lo;
+          peer_hi = peer_hi < it_hi ? peer_hi : it_hi;
+        }
+        const bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
         for (long long t = t0; t < t1; ++t) {
+          if (throttle && ((t - t0) & 7) == 0) {
+            const int mine = (int)(t - t0);
+            asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(mine) : "memory");
+            unsigned long long w0 = 0;
+            for (;;) {
+              int mn = 0x7fffffff;
+              for (int v = peer_lo; v < peer_hi; ++v) {
+                int pv;
+                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(p.progress + v) : "memory");
+                mn = pv < mn ? pv : mn;
+              }
+              if (mine - mn <= kLeadTiles) break;
+              __nanosleep(500);
+              unsigned long long now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (w0 == 0) w0 = now;
+              else if (now - w0 > kWaitLimitNs) break;  // never deadlock on a peer: give up throttling
+            }
+          }
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&sh->empty[stage], phase ^ 1u, p.status, 100 + stage);
             unsigned char* sa = smem + (size_t)stage * kStageBytes;
@@ -372,6 +400,8 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
+        if (throttle)  // finished: never hold a peer back
+          asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(0x3fffffff) : "memory");
       }
     }
   } else if (warp == kMmaWarp) {
