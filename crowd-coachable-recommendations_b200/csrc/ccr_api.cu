@@ -172,10 +172,13 @@ void ccr_set_profile_events(void* start_event, void* stop_event) {
 }
 
 int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k) {
-  (void)n_items; (void)D; (void)k;
-  // B <= 8: one SIMT pass streams the table once with plain 128-bit loads; above that the
-  // tensor-core kernel reads it once for 128 rows at a time.
-  return B <= kSimtRows ? CCR_ALGO_SIMT : CCR_ALGO_TCGEN05;
+  (void)D; (void)k;
+  // Measured on B200 (8.84M x 768, k=100): the TMA + tcgen05 kernel streams the table faster than
+  // the CUDA-core kernel at every batch size (B=1: 3.0 vs 4.9 ms, B=8: 3.3 vs 5.2 ms) because TMA keeps
+  // far more bytes in flight per SM; the 128 padded MMA rows are free in the HBM-bound regime.  The
+  // CUDA-core kernel remains the choice for tiny tables with a handful of rows, where its launch is
+  // cheaper than building tensor maps and running the persistent pipeline.
+  return (B <= kSimtRows && n_items < 65536) ? CCR_ALGO_SIMT : CCR_ALGO_TCGEN05;
 }
 
 size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int flags) {
@@ -293,6 +296,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
 
   FinalizeParams fp;
   fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S * pl.halves; fp.cand = sp.cand; fp.counts = sp.counts;
+  fp.g_tau = sp.g_tau;
   fp.mask_indptr = (has_mask && nnz > 0) ? sp.mask_indptr : nullptr;
   fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
   fp.id_offset = id_offset; fp.out_scores = out_scores; fp.out_scores64 = out_scores64;

@@ -199,22 +199,33 @@ int launch_overrides(const OverrideParams& p, cudaStream_t st) {
 
 // =======================================================================================
 // Finalize: one block (256 threads) per query row.
-// Entries: dense candidates of every split (64-bit keys) and the row's mask overrides, unified
-// as 96-bit sort keys (hi = ord64(double value), lo = ~id).  Exact k-th largest by MSB-first
-// radix select (<= 12 passes, early exit), winners gathered to shared memory, bitonic sorted,
-// written out.
+// Entries: dense candidates of every stream (64-bit keys) and the row's mask overrides, unified
+// as 96-bit sort keys (hi = ord64(double value), lo = ~id).
+//   1. prefix-sum the stream counts so the candidates can be walked as one flat, fully parallel
+//      index space (one independent global load per entry instead of a serial loop over streams);
+//   2. gather into shared memory every dense candidate at or above the row's shared lower bound
+//      g_tau (the global top-k is a subset of those) plus all overrides;
+//   3. exact k-th largest by MSB-first radix select (<= 12 passes, early exit) in shared memory,
+//      winners compacted, bitonic sorted, written out.
+// If the gathered list does not fit (loose bound), the select runs over global memory instead.
 // =======================================================================================
+constexpr int kFinList = 4096;     // shared-memory entry list capacity
+constexpr int kFinMaxStreams = 1024;
+
 struct RowEntries {
-  const u64* cand; const int* counts; int S, C;
+  const u64* cand; const int* prefix; int S, C, total;
   const u64* ovr_hi; const u32* ovr_lo; long long obeg, oend;
+  const u64* l_hi; const u32* l_lo; int l_n;  // shared-memory list (when l_n >= 0)
   template <class F> __device__ __forceinline__ void for_each(F f) const {
-    for (int u = 0; u < S; ++u) {
-      int n = counts[u];
-      const u64* b = cand + (long long)u * C;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        u64 key = b[i];
-        f(ord64((double)key_score(key)), (u32)key);
-      }
+    if (l_n >= 0) {
+      for (int i = threadIdx.x; i < l_n; i += blockDim.x) f(l_hi[i], l_lo[i]);
+      return;
+    }
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      int lo = 0, hi = S;  // stream u with prefix[u] <= i < prefix[u+1]
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= i) lo = mid; else hi = mid; }
+      const u64 key = cand[(long long)lo * C + (i - prefix[lo])];
+      f(ord64((double)key_score(key)), (u32)key);
     }
     for (long long e = obeg + threadIdx.x; e < oend; e += blockDim.x) {
       u64 h = ovr_hi[e];
@@ -223,34 +234,92 @@ struct RowEntries {
   }
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /*pow2 >= k*/) {
+constexpr int kFinMaxThreads = 1024;
+
+__global__ void __launch_bounds__(kFinMaxThreads) finalize_kernel(FinalizeParams p, int P /*pow2 >= k*/) {
+  const int NT = blockDim.x;  // 1024 for small batches (latency-bound gather), 256 otherwise
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  u64* s_hi = reinterpret_cast<u64*>(smem_raw);          // [P]
-  u32* s_lo = reinterpret_cast<u32*>(s_hi + P);           // [P]
+  u64* s_hi = reinterpret_cast<u64*>(smem_raw);                 // [kFinList]
+  u32* s_lo = reinterpret_cast<u32*>(s_hi + kFinList);          // [kFinList]
+  int* s_prefix = reinterpret_cast<int*>(s_lo + kFinList);      // [kFinMaxStreams + 1]
   __shared__ u32 hist[256];
-  __shared__ int s_total, s_nwin;
+  __shared__ int s_nwin, s_nlist, s_warp_sums[32];
   __shared__ u32 s_d, s_need, s_binc;
 
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = p.S;
+  // ---- 1. exclusive prefix sums of the stream counts (<= 4 streams per thread, S <= 1024) ----
+  {
+    const int per = (S + NT - 1) / NT;
+    int loc[4], mine = 0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int u = tid * per + t;
+      loc[t] = (t < per && u < S) ? p.counts[(long long)row * S + u] : 0;
+      mine += loc[t];
+    }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    if (lane == 31) s_warp_sums[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_warp_sums[w];
+    int run = base + incl - mine;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int u = tid * per + t;
+      if (t < per && u < S) { s_prefix[u] = run; run += loc[t]; }
+    }
+    if (tid == NT - 1) s_prefix[S] = base + incl;
+    if (tid == 0) { s_nwin = 0; s_nlist = 0; }
+    __syncthreads();
+  }
   RowEntries E;
-  E.cand = p.cand + (long long)row * p.S * p.C;
-  E.counts = p.counts + (long long)row * p.S;
-  E.S = p.S; E.C = p.C;
+  E.cand = p.cand + (long long)row * S * p.C;
+  E.prefix = s_prefix; E.S = S; E.C = p.C; E.total = s_prefix[S];
   E.ovr_hi = p.ovr_hi; E.ovr_lo = p.ovr_lo;
   E.obeg = p.mask_indptr ? p.mask_indptr[row] : 0;
   E.oend = p.mask_indptr ? p.mask_indptr[row + 1] : 0;
-
-  if (tid == 0) { s_total = 0; s_nwin = 0; }
-  for (int i = tid; i < P; i += 256) { s_hi[i] = 0ull; s_lo[i] = 0u; }
-  __syncthreads();
-  {
-    int local = 0;
-    E.for_each([&](u64, u32) { ++local; });
-    atomicAdd(&s_total, local);
-  }
-  __syncthreads();
-  const int total = s_total;
+  E.l_hi = s_hi; E.l_lo = s_lo; E.l_n = -1;
   const int k = p.k;
+
+  // ---- 2. gather (prefiltered) into shared memory ----
+  {
+    const u32 tau = p.g_tau ? p.g_tau[row] : 0u;  // ord32 lower bound of the k-th best DENSE score
+    // 4 independent loads in flight per thread: the entries live in L2/HBM, latency-bound otherwise
+    for (int i0 = tid; i0 < E.total; i0 += 4 * NT) {
+      u64 key[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = i0 + b * NT;
+        key[b] = 0ull;
+        if (i < E.total) {
+          int lo = 0, hi = S;
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (s_prefix[mid] <= i) lo = mid; else hi = mid; }
+          key[b] = __ldcg(E.cand + (long long)lo * p.C + (i - s_prefix[lo]));
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (i0 + b * NT < E.total && (u32)(key[b] >> 32) >= tau) {
+          int pos = atomicAdd(&s_nlist, 1);
+          if (pos < kFinList) { s_hi[pos] = ord64((double)key_score(key[b])); s_lo[pos] = (u32)key[b]; }
+        }
+      }
+    }
+    for (long long e = E.obeg + tid; e < E.oend; e += NT) {  // overrides are never filtered
+      const u64 h = p.ovr_hi[e];
+      if (h) {
+        int pos = atomicAdd(&s_nlist, 1);
+        if (pos < kFinList) { s_hi[pos] = h; s_lo[pos] = p.ovr_lo[e]; }
+      }
+    }
+    __syncthreads();
+    if (s_nlist <= kFinList) E.l_n = s_nlist;  // fits: everything below runs on shared memory
+    __syncthreads();
+  }
+  const int total = E.l_n >= 0 ? E.l_n : (int)(E.total + (E.oend - E.obeg));
 
   u64 phi = 0, mhi = 0;  // prefix over hi
   u32 plo = 0, mlo = 0;  // prefix over lo
@@ -258,7 +327,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /
   if (!select_all) {
     int need = k;
     for (int pass = 0; pass < 12; ++pass) {
-      hist[tid] = 0;
+      if (tid < 256) hist[tid] = 0;
       __syncthreads();
       const int sh = pass < 8 ? 56 - 8 * pass : 24 - 8 * (pass - 8);
       E.for_each([&](u64 hi, u32 lo) {
@@ -301,8 +370,12 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /
     }
   }
   __syncthreads();
-  // winners: key > prefix-extended threshold.  With early exit the pivot is "all keys whose
-  // masked bits >= prefix", i.e. compare on the masked part only.
+  // winners: masked key bits >= prefix.  They are compacted into a second region so the source
+  // list is not overwritten while it is still being read.
+  u64* w_hi = reinterpret_cast<u64*>(s_prefix + kFinMaxStreams + 2);  // [P], 8-byte aligned (see launcher)
+  u32* w_lo = reinterpret_cast<u32*>(w_hi + P);
+  for (int i = tid; i < P; i += NT) { w_hi[i] = 0ull; w_lo[i] = 0u; }
+  __syncthreads();
   E.for_each([&](u64 hi, u32 lo) {
     bool win;
     if (select_all) win = true;
@@ -312,33 +385,33 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /
     }
     if (win) {
       int pos = atomicAdd(&s_nwin, 1);
-      if (pos < P) { s_hi[pos] = hi; s_lo[pos] = lo; }
+      if (pos < P) { w_hi[pos] = hi; w_lo[pos] = lo; }
     }
   });
   __syncthreads();
   // bitonic sort, descending by (hi, lo); padding entries are (0,0) = smallest
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = tid; t < (P >> 1); t += 256) {
+      for (int t = tid; t < (P >> 1); t += NT) {
         int i = 2 * t - (t & (stride - 1));
         int j = i + stride;
         bool desc = ((i & size) == 0);
-        u64 hi_i = s_hi[i], hi_j = s_hi[j];
-        u32 lo_i = s_lo[i], lo_j = s_lo[j];
+        u64 hi_i = w_hi[i], hi_j = w_hi[j];
+        u32 lo_i = w_lo[i], lo_j = w_lo[j];
         bool i_lt_j = (hi_i < hi_j) || (hi_i == hi_j && lo_i < lo_j);
-        if (i_lt_j == desc) { s_hi[i] = hi_j; s_hi[j] = hi_i; s_lo[i] = lo_j; s_lo[j] = lo_i; }
+        if (i_lt_j == desc) { w_hi[i] = hi_j; w_hi[j] = hi_i; w_lo[i] = lo_j; w_lo[j] = lo_i; }
       }
       __syncthreads();
     }
   }
   const int nwin = min(s_nwin, k);
-  for (int i = tid; i < k; i += 256) {
+  for (int i = tid; i < k; i += NT) {
     long long o = (long long)row * k + i;
     if (i < nwin) {
-      double v = unord64(s_hi[i]);
+      double v = unord64(w_hi[i]);
       if (p.out_scores) p.out_scores[o] = (float)v;
       if (p.out_scores64) p.out_scores64[o] = v;
-      p.out_ids[o] = (long long)(0xFFFFFFFFu - s_lo[i]) + p.id_offset;
+      p.out_ids[o] = (long long)(0xFFFFFFFFu - w_lo[i]) + p.id_offset;
     } else {
       if (p.out_scores) p.out_scores[o] = -INFINITY;
       if (p.out_scores64) p.out_scores64[o] = -INFINITY;
@@ -348,14 +421,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams p, int P /
 }
 
 int launch_finalize(const FinalizeParams& p, cudaStream_t st) {
+  if (p.S > kFinMaxStreams) return (int)cudaErrorInvalidValue;
   int P = 32;
   while (P < p.k) P <<= 1;
-  size_t smem = (size_t)P * 12;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
-  finalize_kernel<<<p.B, 256, smem, st>>>(p, P);
+  // list (12 B/entry) + prefix (kFinMaxStreams + 2 ints, keeps the winner region 8-byte aligned) + winners
+  size_t smem = (size_t)kFinList * 12 + (size_t)(kFinMaxStreams + 2) * 4 + (size_t)P * 12;
+  cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  finalize_kernel<<<p.B, p.B <= 296 ? kFinMaxThreads : 256, smem, st>>>(p, P);
   return (int)cudaGetLastError();
 }
 

@@ -51,6 +51,7 @@ struct FinalizeParams {
   int S;
   const u64* cand;
   const int* counts;
+  const u32* g_tau;  // per-row lower bound of the k-th best dense score (ord32), or null: prefilter
   // mask overrides (null when no mask): per mask entry e, value and ~col
   const long long* mask_indptr;
   const u64* ovr_hi;

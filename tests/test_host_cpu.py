@@ -38,6 +38,7 @@ def test_planning_entry_points_work_without_gpu():
     assert L.ccr_score_topk_workspace_bytes(4, 100, 63, 5, 0, 0) == 0       # D % 8 != 0 -> invalid
     assert L.ccr_score_topk_workspace_bytes(4, 100, 64, 5000, 0, 0) == 0    # k > CCR_MAX_K
     assert L.ccr_choose_algo(4, 1000, 768, 10) == _lib.ALGO_SIMT
+    assert L.ccr_choose_algo(4, 8841823, 768, 100) == _lib.ALGO_TCGEN05
     assert L.ccr_choose_algo(512, 1000, 768, 10) == _lib.ALGO_TCGEN05
     info = _lib.plan_info(4096, 8841823, 768, 100)
     assert info["n_q_tiles"] == 32 and info["cand_capacity"] == 384 and info["n_splits"] >= 5
