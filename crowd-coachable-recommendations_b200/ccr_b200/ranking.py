@@ -120,3 +120,20 @@ def ranking(corpus, queries, embedding_func, batch_size, block_dict=None, device
     for step, qid in enumerate(queries_ids):
         ranking_profile[qid] = dict(zip(corpus_arr[order[step]].tolist(), scores[step].tolist()))
     return ranking_profile
+
+
+def mrr_at_k(order, corpus_ids, queries_ids, qrels, k_values=(1, 5, 10, 100)):
+    """MRR@k of a ranking produced by ``ranking_tensors`` (positions [Q, k], descending), the
+    metric scripts/al_0_rank.py:130-133 obtains from BEIR's ``evaluate_custom(..., metric="mrr")``:
+    per query the reciprocal rank of the first relevant passage (qrels score > 0) within the top
+    k, averaged over queries, rounded to 5 digits.  Vectorised over queries."""
+    pos = {pid: i for i, pid in enumerate(corpus_ids)}
+    Q, K = order.shape
+    first = np.full(Q, np.inf)
+    for qi, qid in enumerate(queries_ids):
+        rel = [pos[p] for p, s in qrels.get(qid, {}).items() if s > 0 and p in pos]
+        if rel:
+            hit = np.nonzero(np.isin(order[qi], rel))[0]
+            if hit.size:
+                first[qi] = hit[0] + 1
+    return {f"MRR@{k}": round(float(np.mean(np.where(first <= k, 1.0 / first, 0.0))), 5) for k in k_values}

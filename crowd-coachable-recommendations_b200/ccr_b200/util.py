@@ -75,3 +75,31 @@ def _assign_topk(S, k, tie_breaker=1e-10, device="cpu", batch_size=None):
 
 
 assign_topk = _assign_topk
+
+
+def _argsort(S, tie_breaker=1e-10, device="cpu"):
+    """Drop-in for ``rime_lite.util._argsort`` (src/rime_lite/util/__init__.py:158-184): global flat
+    argsort of the whole score matrix, best score first, returned as ``(row_idx, col_idx)``.
+
+    For the hot-path expression shape the dense fp32 scores are produced on the device by
+    ``ccr_score_dense_f32`` (+ the sparse term), then ordered with one device sort (a library
+    radix sort: this sibling API is only used on small reranking sets and is not a hot path,
+    SURVEY.md §8 a11).  Ties are ordered by flat position (the reference adds unseeded jitter)."""
+    if not isinstance(S, LazyScoreBase):
+        S = auto_cast_lazy_score(S)
+    plan = fused_plan(S)
+    if plan is None:
+        raise NotImplementedError(f"_argsort: expression {S!r} is outside the accelerated score-and-rank path")
+    table = _device_table_for(plan.right)
+    dense = table.dense_scores(torch.as_tensor(np.ascontiguousarray(plan.left.c)))
+    if plan.sparse is not None:
+        coo = plan.sparse.tocoo()
+        dense = dense.double()
+        dense.index_put_((torch.as_tensor(coo.row, dtype=torch.int64, device=dense.device),
+                          torch.as_tensor(coo.col, dtype=torch.int64, device=dense.device)),
+                         torch.as_tensor(coo.data, dtype=torch.float64, device=dense.device), accumulate=True)
+    order = torch.sort(dense.reshape(-1), descending=True, stable=True).indices.cpu().numpy()
+    return np.unravel_index(order, plan.shape)
+
+
+argsort = _argsort

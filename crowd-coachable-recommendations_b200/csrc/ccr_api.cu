@@ -85,6 +85,10 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
     pl->rows_pad = pl->n_q_tiles * kQTile;
     long long tiles = (n_items + kITile - 1) / kITile;
     pl->S = splits_tc(pl->n_q_tiles, tiles, sms);
+    if (const char* m = getenv("CCR_SPLIT_MULT")) {  // experiment knob: finer units (more waves)
+      long long s2 = (long long)pl->S * atoi(m);
+      if (s2 >= 1 && s2 <= tiles && s2 * 2 <= 1024) pl->S = (int)s2;
+    }
     pl->halves = 2;
     pl->C = cand_capacity(k, 128);
     {
@@ -126,10 +130,13 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
   pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
   pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
   if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !getenv("CCR_NO_SEED")) {
-    // strided sample of ~N/256 items (4096..65536), capped so the fp32 score matrix stays <= 512 MB
+    // strided sample of max(N/256, 64k) items (4096..131072, <= N/8), capped so the fp32 score matrix
+    // stays <= 512 MB
     long long m = n_items / 256;
+    if (m < 64LL * k) m = 64LL * k;  // the (k+h)-th best of the sample should sit in its top ~1.5 %
     if (m < 4096) m = 4096;
-    if (m > 65536) m = 65536;
+    if (m > 131072) m = 131072;
+    if (m > n_items / 8) m = n_items / 8;
     long long cap = (512LL << 20) / (4LL * pl->rows_pad);
     if (m > cap) m = cap;
     m = m / 256 * 256;

@@ -229,6 +229,9 @@ __device__ __forceinline__ u64 warp_prune(u64* buf, int n, int k, u32 hist_s, u3
 //   out_kept      : survivors, compacted to buf[0, kept)
 //   out_j_ord     : ord32 value with at least j keys >= it
 // ---------------------------------------------------------------------------------------
+// kStaged: keys are first copied to shared memory (stage_s) and the later passes read them there;
+// otherwise (buffers larger than the staging area) every pass streams the keys from global memory.
+template <bool kStaged>
 __device__ __forceinline__ bool warp_prune_hist(u64* buf, int n, int k, int j, int max_keep, u32 hist_s,
                                                 u32 stage_s, u32* out_pivot_ord, int* out_kept, u32* out_j_ord) {
   const int lane = threadIdx.x & 31;
@@ -236,7 +239,7 @@ __device__ __forceinline__ bool warp_prune_hist(u64* buf, int n, int k, int j, i
   u32 mx = 0u, mn = 0xFFFFFFFFu;
   for (int i = lane; i < n; i += 32) {
     const u64 key = buf[i];
-    sm_st64(stage_s + (u32)i * 8u, key);
+    if (kStaged) sm_st64(stage_s + (u32)i * 8u, key);
     const u32 o = (u32)(key >> 32);
     mx = o > mx ? o : mx;
     mn = o < mn ? o : mn;
@@ -256,7 +259,7 @@ __device__ __forceinline__ bool warp_prune_hist(u64* buf, int n, int k, int j, i
   for (int t = 0; t < 8; ++t) sm_st32(hist_s + (u32)(lane * 8 + t) * 4u, 0u);
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
-    const u32 o = (u32)(sm_ld64(stage_s + (u32)i * 8u) >> 32);
+    const u32 o = kStaged ? (u32)(sm_ld64(stage_s + (u32)i * 8u) >> 32) : (u32)(buf[i] >> 32);
     sm_red_inc(hist_s + ((o >> shift) - base) * 4u);
   }
   __syncwarp();
@@ -291,17 +294,18 @@ __device__ __forceinline__ bool warp_prune_hist(u64* buf, int n, int k, int j, i
   if ((int)cum_k > max_keep) return false;
   u32 pivot_ord = (base + bin_k) << shift;
   if (pivot_ord < 0x00800000u) pivot_ord = 0x00800000u;  // never below ord32(-FLT_MAX): stays a finite float
-  // compaction stage -> buf (stable)
+  // stable compaction to buf[0, kept); in place it only ever writes at or below the index it read
   int wbase = 0;
   for (int i0 = 0; i0 < n; i0 += 32) {
     const int i = i0 + lane;
-    const u64 key = (i < n) ? sm_ld64(stage_s + (u32)i * 8u) : 0ull;
+    const u64 key = (i < n) ? (kStaged ? sm_ld64(stage_s + (u32)i * 8u) : buf[i]) : 0ull;
     const bool keep = (i < n) && ((u32)(key >> 32) >= pivot_ord);
     const unsigned m = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
     if (keep) buf[wbase + __popc(m & ((1u << lane) - 1u))] = key;
     wbase += __popc(m);
+    __syncwarp();
   }
-  __syncwarp();
   *out_pivot_ord = pivot_ord;
   *out_kept = wbase;
   u32 j_ord = (base + bin_j) << shift;

@@ -281,8 +281,11 @@ static __device__ __noinline__ u64 prune_stream(u64* b, int n, int k, int C, int
   int kept = k;
   u32 j_ord = 0u, pivot_ord = 0u;
   // fast path: one histogram pass; leaves between k and (k + C-128)/2 survivors
-  const bool fast = staged && !(debug & 64) &&
-                    warp_prune_hist(b, n, k, jj, (k + C - 128) / 2, hist_s, stage_s, &pivot_ord, &kept, &j_ord);
+  bool fast = false;
+  if (!(debug & 64)) {
+    if (staged) fast = warp_prune_hist<true>(b, n, k, jj, (k + C - 128) / 2, hist_s, stage_s, &pivot_ord, &kept, &j_ord);
+    else fast = warp_prune_hist<false>(b, n, k, jj, (k + C - 128) / 2, hist_s, stage_s, &pivot_ord, &kept, &j_ord);
+  }
   if (fast) {
     new_tau = unord32(pivot_ord);  // ">=": every key at or above the pivot bucket was kept
   } else {

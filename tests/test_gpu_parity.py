@@ -198,3 +198,70 @@ def test_property_full_size_sample(ccr):
     re = (q[:4].float() @ items[i2[:4].reshape(-1)].float().T)
     re = torch.stack([re[r, r * k:(r + 1) * k] for r in range(4)])
     torch.testing.assert_close(re, s2[:4], rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("name", list(cases.RIME_CASES))
+def test_argsort_dropin_vs_golden(ccr, name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"rime_{name}.npz"))
+    c = cases.rime_case(name)
+    S = ccr.LazyDenseMatrix(c["U"]) @ ccr.LazyDenseMatrix(c["V"]).T
+    if c["prior"] is not None:
+        S = S + c["prior"]
+    r, col = ccr._argsort(S, tie_breaker=0)
+    assert len(r) == S.shape[0] * S.shape[1]
+    dense = O.lazy_score_dense_ref(c["U"], c["V"], c["prior"]).numpy().astype(np.float64)
+    got = dense[r, col]
+    scale = np.abs(dense[np.abs(dense) < 1e4]).max()
+    # descending up to the bf16 tolerance, and the head agrees with the reference's own order
+    assert np.all(np.diff(got) <= RTOL * scale + RTOL * np.abs(got[1:]))
+    agree = np.mean((r[:64] == g["argsort_rows"]) & (col[:64] == g["argsort_cols"]))
+    assert agree > 0.5
+
+
+def test_mrr_matches_manual(ccr):
+    order = np.array([[3, 1, 2], [0, 2, 1], [2, 0, 1]])
+    corpus_ids, qids = ["a", "b", "c", "d"], ["q0", "q1", "q2"]
+    qrels = {"q0": {"b": 1}, "q1": {"d": 1}, "q2": {"c": 1, "a": 0}}
+    m = ccr.mrr_at_k(order, corpus_ids, qids, qrels, k_values=(1, 3))
+    assert m == {"MRR@1": round(1 / 3, 5), "MRR@3": round((0.5 + 0 + 1) / 3, 5)}
+
+
+def test_empty_shard_pads(ccr):
+    dev = torch.device("cuda:0")
+    q = torch.randn(5, 64, device=dev).to(torch.bfloat16)
+    items = torch.zeros(0, 64, device=dev, dtype=torch.bfloat16)
+    s, i = ccr.score_topk(q, items, 7, allow_short=True)
+    assert bool((i == -1).all()) and bool(torch.isinf(s).all())
+    items = torch.randn(3, 64, device=dev).to(torch.bfloat16)
+    s, i = ccr.score_topk(q, items, 7, allow_short=True, id_offset=100)
+    assert bool((i[:, :3] >= 100).all()) and bool((i[:, 3:] == -1).all())
+
+
+def test_full_corpus_properties(ccr):
+    """BASELINE size (8,841,823 x 768), B=300, k=100 with history mask: order, uniqueness, no
+    blocked id returned, every returned score equals the recomputed dot product, and the k-th
+    score dominates a random sample of non-returned items."""
+    dev = torch.device("cuda:0")
+    N, D, B, k = 8_841_823, 768, 300, 100
+    items = torch.empty((N, D), dtype=torch.bfloat16, device=dev)
+    g = torch.Generator(device=dev).manual_seed(11)
+    for s0 in range(0, N, 1 << 20):
+        e = min(N, s0 + (1 << 20))
+        items[s0:e] = torch.randn((e - s0, D), generator=g, device=dev).to(torch.bfloat16)
+    q = torch.randn((B, D), generator=g, device=dev).to(torch.bfloat16)
+    rs = np.random.RandomState(3)
+    rows = [np.unique(rs.randint(0, N, size=rs.randint(0, 65))) for _ in range(B)]
+    # make the mask bite: block each row's true best item as well
+    s0_, i0_ = ccr.score_topk(q, items, 1)
+    rows = [np.unique(np.append(r, int(i0_[b, 0]))) for b, r in enumerate(rows)]
+    mask = ccr.SparseMask.from_lists(rows, N, -1e6, ccr.MASK_SET, dev)
+    s, i = ccr.score_topk(q, items, k, mask=mask)
+    assert bool((s[:, 1:] <= s[:, :-1]).all())
+    assert all(len(set(r.tolist())) == k for r in i.cpu())
+    for b in range(0, B, 37):
+        assert not set(i[b].tolist()) & set(rows[b].tolist())
+        re = (q[b].float() @ items[i[b]].float().T)
+        torch.testing.assert_close(re, s[b], rtol=1e-4, atol=1e-3)
+        probe = torch.as_tensor(rs.randint(0, N, size=20000), device=dev)
+        probe = probe[~torch.isin(probe, i[b]) & ~torch.isin(probe, torch.as_tensor(rows[b], device=dev))]
+        assert float((q[b].float() @ items[probe].float().T).max()) <= float(s[b, -1]) + 1e-3
