@@ -57,10 +57,10 @@ def lib():
     L.ccr_abi_version.restype = i32
     L.ccr_last_error_string.restype = c.c_char_p
     L.ccr_score_topk_bf16.restype = i32
-    L.ccr_score_topk_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, vp, vp, i64, i32, i64,
+    L.ccr_score_topk_bf16.argtypes = [vp, i64, i64, vp, i64, i64, i32, i32, vp, vp, vp, i64, i64, i32, i64,
                                       vp, vp, vp, vp, sz, i32, vp]
     L.ccr_score_topk_workspace_bytes.restype = sz
-    L.ccr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32, i64, i32]
+    L.ccr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32, i64, i64, i32]
     L.ccr_merge_topk.restype = i32
     L.ccr_merge_topk.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
     L.ccr_ingest_rows_f32.restype = i32
@@ -75,7 +75,7 @@ def lib():
     L.ccr_set_profile_events.argtypes = [vp, vp]
     L.ccr_plan_info.restype = i32
     L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i32, c.POINTER(c.c_int32)]
-    if L.ccr_abi_version() != 1:
+    if L.ccr_abi_version() != 2:
         raise RuntimeError("libccr_b200 ABI version mismatch")
     _lib = L
     return L

@@ -58,6 +58,7 @@ class SparseMask:
         self.nnz = int(indptr[-1])
         self.host = (np.asarray(indptr, dtype=np.int64), np.asarray(cols, dtype=np.int32),
                      np.asarray(vals, dtype=np.float64))
+        self.max_row_nnz = int(np.diff(self.host[0]).max()) if self.n_rows else 0
         self.device = torch.device(device)
         self.indptr = torch.as_tensor(self.host[0]).to(self.device)
         self.cols = torch.as_tensor(self.host[1]).to(self.device)
@@ -73,6 +74,7 @@ class SparseMask:
         self.mode = mode
         self.host = host
         self.nnz = int(host[0][-1])
+        self.max_row_nnz = int(np.diff(host[0]).max()) if self.n_rows else 0
         self.device = indptr.device
         self.indptr, self.cols, self.vals = indptr, cols, vals
         return self
@@ -156,7 +158,8 @@ def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_l
     out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
     out_d = torch.empty((B, k), dtype=torch.float64, device=dev) if want_f64 else None
     with torch.cuda.device(dev):
-        need = L.ccr_score_topk_workspace_bytes(B, N, D, k, nnz, flags)
+        hmax = mask.max_row_nnz if mask is not None else -1
+        need = L.ccr_score_topk_workspace_bytes(B, N, D, k, nnz, hmax, flags)
         if need == 0 and B > 0:
             # invalid shape: let the real call produce the error message
             need = 256
@@ -166,7 +169,7 @@ def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_l
             mask.indptr.data_ptr() if mask is not None else None,
             mask.cols.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
             mask.vals.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
-            nnz, mask.mode if mask is not None else MASK_NONE, int(id_offset),
+            nnz, hmax, mask.mode if mask is not None else MASK_NONE, int(id_offset),
             out_s.data_ptr(), out_d.data_ptr() if want_f64 else None, out_i.data_ptr(),
             ws.data_ptr(), ws.numel(), flags, _stream_ptr(dev))
     _lib.check(rc)

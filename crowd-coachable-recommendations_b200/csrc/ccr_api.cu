@@ -45,6 +45,8 @@ struct Plan {
   int halves;   // candidate buffers per (row, split): 2 for the tensor-core kernel
   int C;
   int share_j, share_m;  // threshold sharing level (0 = off)
+  int include_mask;      // 1: masked items stream through and are dropped in finalize (k + h candidates/row)
+  int k_keep;            // k + h_max in include mode, else k
   int seed_m;            // sampled items of the threshold-seeding pre-pass (0 = off)
   long long seed_stride; // item-row stride of the sample
   long long seed_ld;     // row pitch of the sampled score matrix (floats)
@@ -74,11 +76,15 @@ int splits_tc(int nq, long long tiles, int sms) {
   return (int)best;
 }
 
-bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int flags, Plan* pl) {
+// h_max: largest number of mask entries in one row, or < 0 when unknown / no mask
+bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long long h_max, int flags, Plan* pl) {
   int algo = flags & CCR_ALGO_MASK;
   if (algo == CCR_ALGO_AUTO) algo = ccr_choose_algo(B, n_items, D, k);
   const int sms = device_sm_count();
   pl->algo = algo;
+  pl->include_mask = (algo == CCR_ALGO_TCGEN05 && nnz > 0 && h_max >= 0 && h_max <= 256 && k + h_max <= CCR_MAX_K &&
+                      !getenv("CCR_MASK_EXCLUDE")) ? 1 : 0;
+  pl->k_keep = pl->include_mask ? (int)(k + h_max) : k;
   if (algo == CCR_ALGO_TCGEN05) {
     pl->n_q_tiles = (int)((B + kQTile - 1) / kQTile);
     if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
@@ -90,7 +96,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
       if (s2 >= 1 && s2 <= tiles && s2 * 2 <= 1024) pl->S = (int)s2;
     }
     pl->halves = 2;
-    pl->C = cand_capacity(k, 128);
+    pl->C = cand_capacity(pl->k_keep, 128);
     {
       // streams of one row that run in the first wave; use half of them for the bound so a few
       // late streams do not hold it back
@@ -101,10 +107,12 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
       if (s_conc > 256) s_conc = 256;
       int use = s_conc / 2 > 1 ? s_conc / 2 : 1;
       int j = 1;
-      while ((k + j - 1) / j > use) j <<= 1;
+      const int kk = pl->k_keep;  // m * j distinct items must cover k plus every possibly-masked one
+      while ((kk + j - 1) / j > use) j <<= 1;
       if (j > k) j = k;
       pl->share_j = (s_row > 1 && !getenv("CCR_NO_SHARE")) ? j : 0;
-      pl->share_m = (k + j - 1) / j;
+      pl->share_m = (kk + j - 1) / j;
+      if (pl->share_m > 256 || pl->share_m > s_row) pl->share_j = 0;
     }
   } else {
     pl->n_q_tiles = (int)((B + kSimtRows - 1) / kSimtRows);
@@ -133,14 +141,14 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, int 
     // strided sample of max(N/256, 64k) items (4096..131072, <= N/8), capped so the fp32 score matrix
     // stays <= 512 MB
     long long m = n_items / 256;
-    if (m < 64LL * k) m = 64LL * k;  // the (k+h)-th best of the sample should sit in its top ~1.5 %
+    if (m < 64LL * pl->k_keep) m = 64LL * pl->k_keep;  // the (k+h)-th best of the sample should sit in its top ~1.5 %
     if (m < 4096) m = 4096;
     if (m > 131072) m = 131072;
     if (m > n_items / 8) m = n_items / 8;
     long long cap = (512LL << 20) / (4LL * pl->rows_pad);
     if (m > cap) m = cap;
     m = m / 256 * 256;
-    if (m >= 1024 && 4LL * k <= m) {
+    if (m >= 1024 && 4LL * pl->k_keep <= m) {
       pl->seed_m = (int)m;
       pl->seed_stride = n_items / m;
       pl->seed_ld = m;
@@ -188,10 +196,11 @@ int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k) {
   return (B <= kSimtRows && n_items < 65536) ? CCR_ALGO_SIMT : CCR_ALGO_TCGEN05;
 }
 
-size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int flags) {
+size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz,
+                                      int64_t mask_max_row_nnz, int flags) {
   if (check_shape(B, n_items, D, k, flags | CCR_FLAG_ALLOW_SHORT) != CCR_OK) return 0;
   Plan pl;
-  make_plan(B, n_items, D, k, mask_nnz, flags, &pl);
+  make_plan(B, n_items, D, k, mask_nnz, mask_nnz > 0 ? mask_max_row_nnz : -1, flags, &pl);
   return pl.total;
 }
 
@@ -200,7 +209,7 @@ int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* 
   if (rc) return rc;
   if (!info4) return fail(CCR_EINVAL, "info4 is null");
   Plan pl;
-  make_plan(B, n_items, D, k, 0, flags, &pl);
+  make_plan(B, n_items, D, k, 0, -1, flags, &pl);
   info4[0] = pl.n_q_tiles;
   info4[1] = pl.S;
   info4[2] = pl.C;
@@ -210,8 +219,8 @@ int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* 
 
 int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
                         int64_t ldi, int D, int k, const int64_t* mask_indptr, const int32_t* mask_cols,
-                        const double* mask_vals, int64_t mask_nnz, int mask_mode, int64_t id_offset,
-                        float* out_scores,
+                        const double* mask_vals, int64_t mask_nnz, int64_t mask_max_row_nnz, int mask_mode,
+                        int64_t id_offset, float* out_scores,
                         double* out_scores64, int64_t* out_ids, void* workspace, size_t workspace_bytes,
                         int flags, void* stream) {
   int rc = check_shape(B, n_items, D, k, flags);
@@ -230,7 +239,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   const long long nnz = has_mask ? mask_nnz : 0;
   if (nnz < 0) return fail(CCR_EINVAL, "mask_nnz = %lld", nnz);
   Plan pl;
-  make_plan(B, n_items, D, k, nnz, flags, &pl);
+  make_plan(B, n_items, D, k, nnz, nnz > 0 ? mask_max_row_nnz : -1, flags, &pl);
   if (!workspace || workspace_bytes < pl.total)
     return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, pl.total);
   unsigned char* ws = (unsigned char*)workspace;
@@ -244,7 +253,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
   sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles;
   sp.mask_indptr = has_mask ? (const long long*)mask_indptr : nullptr;
-  sp.mask_cols = has_mask ? mask_cols : nullptr;
+  sp.mask_cols = (has_mask && !pl.include_mask) ? mask_cols : nullptr;
   sp.cand = (u64*)(ws + pl.off_cand);
   sp.counts = (int*)(ws + pl.off_counts);
   sp.status = status;
@@ -304,6 +313,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   FinalizeParams fp;
   fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S * pl.halves; fp.cand = sp.cand; fp.counts = sp.counts;
   fp.g_tau = sp.g_tau;
+  fp.drop_cols = (has_mask && nnz > 0 && pl.include_mask) ? mask_cols : nullptr;
   fp.mask_indptr = (has_mask && nnz > 0) ? sp.mask_indptr : nullptr;
   fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
   fp.id_offset = id_offset; fp.out_scores = out_scores; fp.out_scores64 = out_scores64;

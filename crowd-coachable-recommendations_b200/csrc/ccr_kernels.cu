@@ -216,6 +216,7 @@ struct RowEntries {
   const u64* cand; const int* prefix; int S, C, total;
   const u64* ovr_hi; const u32* ovr_lo; long long obeg, oend;
   const u64* l_hi; const u32* l_lo; int l_n;  // shared-memory list (when l_n >= 0)
+  const int* drop_cols;                        // include mode: skip dense candidates in the row's mask
   template <class F> __device__ __forceinline__ void for_each(F f) const {
     if (l_n >= 0) {
       for (int i = threadIdx.x; i < l_n; i += blockDim.x) f(l_hi[i], l_lo[i]);
@@ -225,6 +226,7 @@ struct RowEntries {
       int lo = 0, hi = S;  // stream u with prefix[u] <= i < prefix[u+1]
       while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (prefix[mid] <= i) lo = mid; else hi = mid; }
       const u64 key = cand[(long long)lo * C + (i - prefix[lo])];
+      if (drop_cols && mask_contains(drop_cols, obeg, oend, (int)key_id(key))) continue;
       f(ord64((double)key_score(key)), (u32)key);
     }
     for (long long e = obeg + threadIdx.x; e < oend; e += blockDim.x) {
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(kFinMaxThreads) finalize_kernel(FinalizeParams
   E.obeg = p.mask_indptr ? p.mask_indptr[row] : 0;
   E.oend = p.mask_indptr ? p.mask_indptr[row + 1] : 0;
   E.l_hi = s_hi; E.l_lo = s_lo; E.l_n = -1;
+  E.drop_cols = p.drop_cols;
   const int k = p.k;
 
   // ---- 2. gather (prefiltered) into shared memory ----
@@ -302,7 +305,9 @@ __global__ void __launch_bounds__(kFinMaxThreads) finalize_kernel(FinalizeParams
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        if (i0 + b * NT < E.total && (u32)(key[b] >> 32) >= tau) {
+        bool take = i0 + b * NT < E.total && (u32)(key[b] >> 32) >= tau;
+        if (take && p.drop_cols) take = !mask_contains(p.drop_cols, E.obeg, E.oend, (int)key_id(key[b]));
+        if (take) {
           int pos = atomicAdd(&s_nlist, 1);
           if (pos < kFinList) { s_hi[pos] = ord64((double)key_score(key[b])); s_lo[pos] = (u32)key[b]; }
         }
@@ -319,7 +324,15 @@ __global__ void __launch_bounds__(kFinMaxThreads) finalize_kernel(FinalizeParams
     if (s_nlist <= kFinList) E.l_n = s_nlist;  // fits: everything below runs on shared memory
     __syncthreads();
   }
-  const int total = E.l_n >= 0 ? E.l_n : (int)(E.total + (E.oend - E.obeg));
+  if (E.l_n < 0) {  // list overflow: count the surviving entries over global memory
+    if (tid == 0) s_nlist = 0;
+    __syncthreads();
+    int local = 0;
+    E.for_each([&](u64, u32) { ++local; });
+    atomicAdd(&s_nlist, local);
+    __syncthreads();
+  }
+  const int total = E.l_n >= 0 ? E.l_n : s_nlist;
 
   u64 phi = 0, mhi = 0;  // prefix over hi
   u32 plo = 0, mlo = 0;  // prefix over lo

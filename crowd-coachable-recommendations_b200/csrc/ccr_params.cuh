@@ -20,7 +20,9 @@ struct SelectParams {
   int S;          // item splits
   int n_q_tiles;  // query tiles (tensor-core kernel) or query groups (SIMT kernel)
   const long long* mask_indptr;  // null when no mask
-  const int* mask_cols;
+  const int* mask_cols;          // null in 'include' mode (masked items are NOT excluded while
+                                 // streaming: each row keeps k + nnz(row) candidates instead and
+                                 // finalize drops the masked ones); set in 'exclude' mode
   u64* cand;
   int* counts;
   // cross-stream threshold sharing (tensor-core kernel; null/0 = off).  A "stream" is one
@@ -52,6 +54,8 @@ struct FinalizeParams {
   const u64* cand;
   const int* counts;
   const u32* g_tau;  // per-row lower bound of the k-th best dense score (ord32), or null: prefilter
+  const int* drop_cols;  // include mode: the mask's column array; dense candidates found in the row's
+                         // list are dropped here (their override record carries the final value)
   // mask overrides (null when no mask): per mask entry e, value and ~col
   const long long* mask_indptr;
   const u64* ovr_hi;

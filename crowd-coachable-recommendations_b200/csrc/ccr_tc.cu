@@ -150,8 +150,10 @@ struct SelState {
   float tau_f;     // pass iff score >= tau_f: max(next_up(local k-th best), shared row bound),
                    // -inf before the first prune, +inf for padding rows
   long long mbeg, mend;  // the row's slice of the mask CSR
-  u64 sig;         // 64-bit signature of the row's masked columns (bit col & 63)
+  u64 sig;         // signature of the row's masked columns: bit (col & 63) ...
+  u64 sig2;        // ... and bit ((col >> 6) & 63): both must be set before the exact search runs
   int row;         // global query row
+  int k_row;       // candidates this row must keep: k (+ the row's mask entries in include mode)
   int stream;      // index of this stream among the row's streams
   unsigned n_slow, n_prune;  // debug counters (CCR_DEBUG & 4)
 };
@@ -198,7 +200,7 @@ __device__ __forceinline__ void filter_chunk(const u32 (&v)[32], u32 col0, SelSt
   if (kMask) {                                                                                   \
     u32 sb = v[J];                                                                               \
     const u32 col = col0 + (u32)(J);                                                             \
-    if (__uint_as_float(sb) >= st.tau_f && ((st.sig >> (col & 63u)) & 1ull)) {                   \
+    if (__uint_as_float(sb) >= st.tau_f && ((st.sig >> (col & 63u)) & (st.sig2 >> ((col >> 6) & 63u)) & 1ull)) { \
       if (masked_slow(p.mask_cols, st.mbeg, st.mend, (int)col)) sb = 0x7fc00000u;                \
     }                                                                                            \
     append_if_ge<J>(sb, st.tau_f, nlo0, st.buf, st.cnt);                                         \
@@ -319,7 +321,8 @@ __device__ __forceinline__ void prune_pending(SelState& st, const ShareArgs& sh,
     const int n = __shfl_sync(0xffffffffu, st.cnt, src);
     const int row_s = __shfl_sync(0xffffffffu, st.row, src);
     const int stream_s = __shfl_sync(0xffffffffu, st.stream, src);
-    const u64 r = prune_stream(b, n, k, C, row_s, stream_s, sh, hist_s, stage_s, debug);
+    const int k_s = __shfl_sync(0xffffffffu, st.k_row, src);
+    const u64 r = prune_stream(b, n, k_s, C, row_s, stream_s, sh, hist_s, stage_s, debug);
     if (lane == src) { st.cnt = (int)(r >> 32); st.tau_f = __uint_as_float((u32)r); }
   }
 }
@@ -495,11 +498,18 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       st.cnt = 0;
       st.tau_f = (valid_row && !(p.debug & 2)) ? -INFINITY : INFINITY;  // debug 2: reject everything
       if ((p.debug & 16) && valid_row) st.tau_f = p.debug_tau;
-      st.mbeg = 0; st.mend = 0; st.sig = 0ull;
+      st.mbeg = 0; st.mend = 0; st.sig = 0ull; st.sig2 = 0ull;
       st.row = row; st.stream = u * 2 + half;
+      st.k_row = k;
+      if (!kMask && p.mask_indptr && valid_row) st.k_row = k + (int)(p.mask_indptr[row + 1] - p.mask_indptr[row]);
       if (kMask && valid_row) {
         st.mbeg = p.mask_indptr[row]; st.mend = p.mask_indptr[row + 1];
-        for (long long e = st.mbeg; e < st.mend; ++e) st.sig |= 1ull << ((u32)__ldg(p.mask_cols + e) & 63u);
+        for (long long e = st.mbeg; e < st.mend; ++e) {
+          const u32 mc = (u32)__ldg(p.mask_cols + e);
+          st.sig |= 1ull << (mc & 63u);
+          st.sig2 |= 1ull << ((mc >> 6) & 63u);
+        }
+        if (p.debug & 256) { st.sig = 0ull; st.sig2 = 0ull; }  // experiment: never run the exact search
       }
 
       for (long long t = t0; t < t1; ++t) {

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CCR_ABI_VERSION 1
+#define CCR_ABI_VERSION 2
 
 /* error codes */
 #define CCR_OK 0
@@ -76,8 +76,10 @@ const char* ccr_last_error_string(void);
  *   D        embedding dim (768 in the reference: ms_marco_eval.py:190), D % 8 == 0, D <= 4096
  *   k        1 .. CCR_MAX_K
  *   mask_*   CSR over the LOCAL item columns of this shard: indptr[B+1] (int64), cols sorted
- *            and unique per row (int32, < n_items), vals float64, mask_nnz == indptr[B]; all
- *            NULL / 0 when mask_mode == CCR_MASK_NONE
+ *            and unique per row (int32, < n_items), vals float64, mask_nnz == indptr[B];
+ *            mask_max_row_nnz = largest number of entries in one row (lets the kernel stream masked
+ *            items through and drop them at the end instead of testing every candidate; pass -1 if
+ *            unknown); all NULL / 0 when mask_mode == CCR_MASK_NONE
  *   id_offset added to local item ids on output (row-sharded tables)
  *   out_scores   [B, k] float32, descending           (may be NULL)
  *   out_scores64 [B, k] float64 exact value the order was decided on (may be NULL)
@@ -87,8 +89,8 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq,
                         const void* items, int64_t n_items, int64_t ldi,
                         int D, int k,
                         const int64_t* mask_indptr, const int32_t* mask_cols,
-                        const double* mask_vals, int64_t mask_nnz, int mask_mode,
-                        int64_t id_offset,
+                        const double* mask_vals, int64_t mask_nnz, int64_t mask_max_row_nnz,
+                        int mask_mode, int64_t id_offset,
                         float* out_scores, double* out_scores64, int64_t* out_ids,
                         void* workspace, size_t workspace_bytes,
                         int flags, void* stream);
@@ -96,7 +98,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq,
 /* Bytes of workspace ccr_score_topk_bf16 needs for these arguments (same flags!).
  * Returns 0 on invalid arguments. */
 size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k,
-                                      int64_t mask_nnz, int flags);
+                                      int64_t mask_nnz, int64_t mask_max_row_nnz, int flags);
 
 /*
  * G-way merge of per-shard top-k lists after the all-gather (multi-GPU exchange step; no

@@ -38,7 +38,10 @@ mask = None
 if mask_h:
     import numpy as np
     rs = np.random.RandomState(2)
-    rows = [np.unique(rs.randint(0, N, size=min(64, rs.geometric(1.0 / mask_h)))) for _ in range(B)]
+    if mask_h < 0:
+        rows = [np.zeros(0, dtype=np.int64) for _ in range(B)]
+    else:
+        rows = [np.unique(rs.randint(0, N, size=min(64, rs.geometric(1.0 / mask_h)))) for _ in range(B)]
     mask = engine.SparseMask.from_lists(rows, N, -1e6, engine.MASK_SET, dev)
 
 pynvml.nvmlInit()

@@ -37,6 +37,7 @@ def _worker(rank, world, port, ret):
             self.n_rows, self.n_cols, self.mode = len(indptr) - 1, int(n_cols), mode
             self.nnz = int(indptr[-1])
             self.host = (np.asarray(indptr, np.int64), np.asarray(cols, np.int32), np.asarray(vals, np.float64))
+            self.max_row_nnz = int(np.diff(self.host[0]).max()) if self.n_rows else 0
             self.device = None
 
     engine.SparseMask = HostMask

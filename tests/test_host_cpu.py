@@ -26,17 +26,17 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().ccr_abi_version() == 1
+    assert _lib.lib().ccr_abi_version() == 2
 
 
 def test_planning_entry_points_work_without_gpu():
     from ccr_b200 import _lib
 
     L = _lib.lib()
-    assert L.ccr_score_topk_workspace_bytes(4096, 8841823, 768, 100, 0, 0) > 0
-    assert L.ccr_score_topk_workspace_bytes(0, 100, 64, 5, 0, 0) > 0        # B == 0 must not crash
-    assert L.ccr_score_topk_workspace_bytes(4, 100, 63, 5, 0, 0) == 0       # D % 8 != 0 -> invalid
-    assert L.ccr_score_topk_workspace_bytes(4, 100, 64, 5000, 0, 0) == 0    # k > CCR_MAX_K
+    assert L.ccr_score_topk_workspace_bytes(4096, 8841823, 768, 100, 0, -1, 0) > 0
+    assert L.ccr_score_topk_workspace_bytes(0, 100, 64, 5, 0, -1, 0) > 0        # B == 0 must not crash
+    assert L.ccr_score_topk_workspace_bytes(4, 100, 63, 5, 0, -1, 0) == 0       # D % 8 != 0 -> invalid
+    assert L.ccr_score_topk_workspace_bytes(4, 100, 64, 5000, 0, -1, 0) == 0    # k > CCR_MAX_K
     assert L.ccr_choose_algo(4, 1000, 768, 10) == _lib.ALGO_SIMT
     assert L.ccr_choose_algo(4, 8841823, 768, 100) == _lib.ALGO_TCGEN05
     assert L.ccr_choose_algo(512, 1000, 768, 10) == _lib.ALGO_TCGEN05
@@ -131,6 +131,7 @@ def test_mask_helpers_on_cpu_arrays():
             self.mode = mode
             self.nnz = int(indptr[-1])
             self.host = (np.asarray(indptr, np.int64), np.asarray(cols, np.int32), np.asarray(vals, np.float64))
+            self.max_row_nnz = int(np.diff(self.host[0]).max()) if self.n_rows else 0
             self.device = None
 
     engine_SparseMask = engine.SparseMask
