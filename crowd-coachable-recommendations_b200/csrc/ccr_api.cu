@@ -45,6 +45,7 @@ struct Plan {
   int halves;   // candidate buffers per (row, split): 2 for the tensor-core kernel
   int C;
   int share_j, share_m;  // threshold sharing level (0 = off)
+  int two_cta;           // tensor-core kernel variant: CTA pairs (cta_group::2)
   int include_mask;      // 1: masked items stream through and are dropped in finalize (k + h candidates/row)
   int k_keep;            // k + h_max in include mode, else k
   int seed_m;            // sampled items of the threshold-seeding pre-pass (0 = off)
@@ -86,11 +87,19 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
                       !getenv("CCR_MASK_EXCLUDE")) ? 1 : 0;
   pl->k_keep = pl->include_mask ? (int)(k + h_max) : k;
   if (algo == CCR_ALGO_TCGEN05) {
-    pl->n_q_tiles = (int)((B + kQTile - 1) / kQTile);
+    // CTA pairs (cta_group::2, 256 query rows per unit).  Measured on B200 (8.84M x 768, k=100): the
+    // pair streams each item tile once for 256 queries, which wins where the item stream is the
+    // limit (B=256: 3.46 vs 4.07 ms); from B=512 up the two variants tie and at B>=4096 the pair is
+    // 3-5 % slower with selection on (its MMA waits for 16 selection warps instead of 8) although its
+    // GEMM pipeline alone is ~9 % faster.  CCR_2CTA=0/1 overrides.
+    pl->two_cta = (B > kQTile && B <= 3 * kQTile) ? 1 : 0;
+    if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
+    const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
+    pl->n_q_tiles = (int)((B + unit_rows - 1) / unit_rows);
     if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
-    pl->rows_pad = pl->n_q_tiles * kQTile;
+    pl->rows_pad = pl->n_q_tiles * unit_rows;
     long long tiles = (n_items + kITile - 1) / kITile;
-    pl->S = splits_tc(pl->n_q_tiles, tiles, sms);
+    pl->S = splits_tc(pl->n_q_tiles, tiles, pl->two_cta ? sms / 2 : sms);
     if (const char* m = getenv("CCR_SPLIT_MULT")) {  // experiment knob: finer units (more waves)
       long long s2 = (long long)pl->S * atoi(m);
       if (s2 >= 1 && s2 <= tiles && s2 * 2 <= 1024) pl->S = (int)s2;
@@ -101,7 +110,8 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
       // streams of one row that run in the first wave; use half of them for the bound so a few
       // late streams do not hold it back
       int s_row = pl->S * pl->halves;
-      int conc_splits = (sms + pl->n_q_tiles - 1) / pl->n_q_tiles;
+      const int workers = pl->two_cta ? sms / 2 : sms;
+      int conc_splits = (workers + pl->n_q_tiles - 1) / pl->n_q_tiles;
       if (conc_splits > pl->S) conc_splits = pl->S;
       int s_conc = conc_splits * pl->halves;
       if (s_conc > 256) s_conc = 256;
@@ -124,6 +134,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     if (s < 1) s = 1;
     pl->S = (int)s;
     pl->halves = 1;
+    pl->two_cta = 0;
     pl->C = cand_capacity(k, kSimtChunk);
     pl->share_j = 0; pl->share_m = 0;
   }
@@ -251,7 +262,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   SelectParams sp;
   sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B;
   sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
-  sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles;
+  sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles; sp.two_cta = pl.two_cta;
   sp.mask_indptr = has_mask ? (const long long*)mask_indptr : nullptr;
   sp.mask_cols = (has_mask && !pl.include_mask) ? mask_cols : nullptr;
   sp.cand = (u64*)(ws + pl.off_cand);
@@ -280,8 +291,9 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
     ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld;
     ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr;
+    ss.two_cta = 0; ss.n_q_tiles = pl.rows_pad / kQTile;
     long long tiles = (pl.seed_m + kITile - 1) / kITile;
-    ss.S = splits_tc(pl.n_q_tiles, tiles, device_sm_count());
+    ss.S = splits_tc(ss.n_q_tiles, tiles, device_sm_count());
     int lr0 = launch_select_tc(ss, st, device_sm_count());
     if (lr0) return fail(CCR_ECUDA, "seed GEMM launch failed (%d)", lr0);
     lr0 = launch_seed_tau(ss.dense_out, pl.seed_ld, pl.seed_m, (int)B, k, has_mask ? (const long long*)mask_indptr : nullptr,

@@ -18,7 +18,8 @@ struct SelectParams {
   int k;
   int C;          // candidate capacity per (row, split)
   int S;          // item splits
-  int n_q_tiles;  // query tiles (tensor-core kernel) or query groups (SIMT kernel)
+  int n_q_tiles;  // query tiles (tensor-core kernel: 128 rows, or 256 when two_cta) or groups of 8 (SIMT)
+  int two_cta;    // tensor-core kernel: units are CTA pairs (cta_group::2, UMMA M = 256)
   const long long* mask_indptr;  // null when no mask
   const int* mask_cols;          // null in 'include' mode (masked items are NOT excluded while
                                  // streaming: each row keeps k + nnz(row) candidates instead and

@@ -21,10 +21,19 @@
 
 namespace ccr {
 
-constexpr int kStages = 4;
-constexpr int kBytesA = kQTile * kKBlock * 2;   // 16384
-constexpr int kBytesB = kITile * kKBlock * 2;   // 32768
-constexpr int kStageBytes = kBytesA + kBytesB;  // 49152
+constexpr int kMaxStages = 6;
+constexpr int kBytesA = kQTile * kKBlock * 2;   // 16384: 128 query rows x 64 K-elements
+constexpr int kBytesB = kITile * kKBlock * 2;   // 32768: 256 item rows x 64 K-elements
+// kCta = 1: one CTA owns a 128-query tile, loads the whole item block: 48 KB / stage, 4 stages.
+// kCta = 2: a CTA pair (cta_group::2, UMMA M = 256) owns 256 queries; each CTA loads its 128 query
+//           rows and HALF of the item block: 32 KB / stage, 6 stages -> more bytes in flight per SM
+//           and half the item traffic from L2.
+template <int kCta> struct TcGeom {
+  static constexpr int kStages = kCta == 2 ? 6 : 4;
+  static constexpr int kItemBytes = kBytesB / kCta;
+  static constexpr int kStageBytes = kBytesA + kItemBytes;
+  static constexpr int kItemRows = kITile / kCta;
+};
 constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, one per column half
 constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA (the
                                                 // scheduler favours high warp ids: keep the feeders there)
@@ -35,8 +44,8 @@ constexpr int kTmemCols = 512;
 constexpr unsigned long long kWaitLimitNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
 
 struct __align__(8) TcShared {
-  u64 full[kStages];
-  u64 empty[kStages];
+  u64 full[kMaxStages];
+  u64 empty[kMaxStages];
   u64 tmem_full[2];
   u64 tmem_empty[2];
   u32 tmem_base;
@@ -44,7 +53,7 @@ struct __align__(8) TcShared {
   u32 hist[kEpiWarps][256];
   u64 stage[kEpiWarps][kStageKeys];
 };
-constexpr size_t kTcSmemBytes = (size_t)kStages * kStageBytes + sizeof(TcShared) + 1024;
+constexpr size_t kTcSmemBytes = (size_t)4 * (kBytesA + kBytesB) + sizeof(TcShared) + 1024;  // same for both geometries
 
 // ---------------------------------------------------------------------------------------
 // PTX wrappers
@@ -97,6 +106,38 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p`'s offset inside CTA `rank` of this cluster
+__device__ __forceinline__ u32 mapa_u32(const void* p, u32 rank) {
+  u32 r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+// TMA load into OWN shared memory whose bytes are accounted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, int c0, int c1, u32 leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(u64* bar) {  // arrives on `bar`'s offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2cta(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(u32 cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(u64* bar) {
@@ -138,7 +179,9 @@ __device__ __forceinline__ u64 make_sw128_desc(u32 saddr) {
 }
 // instruction descriptor, kind::f16: c_format f32 (bit 4), a/b format bf16 (bits 7, 10),
 // both K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-constexpr u32 kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kITile >> 3) << 17) | ((u32)(kQTile >> 4) << 24);
+template <int kCta> struct TcIdesc {
+  static constexpr u32 value = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kITile >> 3) << 17) | ((u32)((kQTile * kCta) >> 4) << 24);
+};
 
 // ---------------------------------------------------------------------------------------
 // per-thread selection state, the per-chunk filter (32 columns of one query row) and the
@@ -331,12 +374,16 @@ __device__ __forceinline__ void prune_pending(SelState& st, const ShareArgs& sh,
 // the kernel
 // ---------------------------------------------------------------------------------------
 // kMode: 0 select (no mask), 1 select (mask CSR), 2 store fp32 scores (seeding pre-pass)
-template <int kMode>
+template <int kMode, int kCta>
 __global__ void __launch_bounds__(kTcThreads, 1)
 select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_items,
                  SelectParams p) {
+  using G = TcGeom<kCta>;
+  constexpr int kStages = G::kStages;
+  constexpr int kStageBytes = G::kStageBytes;
+  constexpr int kQRows = kQTile * kCta;   // query rows per unit
   extern __shared__ unsigned char smem_dyn[];
-  // 1024-byte alignment for the swizzled tiles
+  // 1024-byte alignment for the swizzled tiles (identical offsets in both CTAs of a pair)
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
   TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)kStages * kStageBytes);
 
@@ -344,21 +391,30 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int num_kb = (p.D + kKBlock - 1) / kKBlock;
   const long long tiles_total = (p.n_items + kITile - 1) / kITile;
   const int n_units = p.n_q_tiles * p.S;
+  const int crank = kCta == 2 ? (int)cluster_ctarank() : 0;   // 0 = leader (issues the MMAs)
+  const int cid = (int)blockIdx.x / kCta, n_cl = (int)gridDim.x / kCta;  // persistent workers = clusters
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full[s], 1); mbar_init(&sh->tmem_empty[s], kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full[s], 1); mbar_init(&sh->tmem_empty[s], kEpiWarps * kCta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_items) : "memory");
   }
   if (warp == kMmaWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"((u32)kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kCta == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"((u32)kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"((u32)kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kCta == 2) cluster_sync_all();  // the peer's barriers exist before anything is signalled on them
   tc_fence_after();
   const u32 tmem_base = sh->tmem_base;
 
@@ -366,13 +422,13 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      for (int unit = cid; unit < n_units; unit += n_cl) {
         const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
         const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
         // peers: units of the same item split scheduled in the same persistent iteration
         int peer_lo = u * p.n_q_tiles, peer_hi = peer_lo + p.n_q_tiles;
         {
-          const int it_lo = (unit / (int)gridDim.x) * (int)gridDim.x, it_hi = it_lo + (int)gridDim.x;
+          const int it_lo = (unit / n_cl) * n_cl, it_hi = it_lo + n_cl;
           peer_lo = peer_lo > it_lo ? peer_lo : it_lo;
           peer_hi = peer_hi < it_hi ? peer_hi : it_hi;
         }
@@ -400,9 +456,17 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&sh->empty[stage], phase ^ 1u, p.status, 100 + stage);
             unsigned char* sa = smem + (size_t)stage * kStageBytes;
-            mbar_expect_tx(&sh->full[stage], kStageBytes);
-            tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
-            tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage]);
+            if (kCta == 2) {
+              // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
+              if (crank == 0) mbar_expect_tx(&sh->full[stage], 2 * kStageBytes);
+              const u32 lbar = mapa_u32(&sh->full[stage], 0);
+              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar);
+              tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar);
+            } else {
+              mbar_expect_tx(&sh->full[stage], kStageBytes);
+              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
+              tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage]);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -411,11 +475,11 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       }
     }
   } else if (warp == kMmaWarp) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (leader CTA only in a pair) =================
+    if (lane == 0 && crank == 0) {
       int stage = 0; u32 phase = 0;
       int acc = 0; u32 acc_phase = 0;
-      for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+      for (int unit = cid; unit < n_units; unit += n_cl) {
         const int u = unit / p.n_q_tiles;
         const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
         for (long long t = t0; t < t1; ++t) {
@@ -431,12 +495,17 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
             for (int kk = 0; kk < kKBlock / 16; ++kk) {
               // +32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units
-              tc_mma_bf16(d_tmem, adesc + (u64)(kk * 2), bdesc + (u64)(kk * 2), kIdesc, (kb | kk) ? 1u : 0u);
+              if (kCta == 2)
+                tc_mma_bf16_2cta(d_tmem, adesc + (u64)(kk * 2), bdesc + (u64)(kk * 2), TcIdesc<2>::value, (kb | kk) ? 1u : 0u);
+              else
+                tc_mma_bf16(d_tmem, adesc + (u64)(kk * 2), bdesc + (u64)(kk * 2), TcIdesc<1>::value, (kb | kk) ? 1u : 0u);
             }
-            tc_commit(&sh->empty[stage]);  // frees the smem slot once these MMAs retire
+            // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+            if (kCta == 2) tc_commit_2cta(&sh->empty[stage]); else tc_commit(&sh->empty[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(&sh->tmem_full[acc]);  // accumulator complete
+          // accumulator complete (both CTAs' selection warps wake up)
+          if (kCta == 2) tc_commit_2cta(&sh->tmem_full[acc]); else tc_commit(&sh->tmem_full[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
       }
@@ -446,10 +515,10 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int quad = warp & 3, half = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; u32 acc_phase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    for (int unit = cid; unit < n_units; unit += n_cl) {
       const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
       const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
-      float* orow = p.dense_out + (long long)(qt * kQTile + row_in_tile) * p.ld_out;
+      float* orow = p.dense_out + (long long)(qt * kQRows + crank * kQTile + row_in_tile) * p.ld_out;
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&sh->tmem_full[acc], acc_phase, p.status, 400 + acc);
         tc_fence_after();
@@ -468,7 +537,10 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+        if (lane == 0) {
+          if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
+          else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -485,10 +557,10 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     ShareArgs sa;
     sa.g_tau = p.g_tau; sa.g_q = p.g_q; sa.S_row = p.S_row; sa.share_j = p.share_j; sa.share_m = p.share_m;
     int acc = 0; u32 acc_phase = 0;
-    for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    for (int unit = cid; unit < n_units; unit += n_cl) {
       const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
       const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
-      const int row = qt * kQTile + row_in_tile;
+      const int row = qt * kQRows + crank * kQTile + row_in_tile;
       const bool valid_row = row < p.B;
       unsigned long long t_start = 0;
       if (p.debug & (4 | 128)) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
@@ -531,9 +603,13 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tmem_ld_32x32b_x32(taddr0 + (u32)(32 * (c + 1)), w);
           } else {
             // every column of this half is in registers: hand the accumulator back to the MMA warp
+            // (of the leader CTA when two CTAs share the MMA)
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+            if (lane == 0) {
+              if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
+              else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+            }
           }
           if (ragged) clamp_ragged(v, col0 + 32 * c, p.n_items);
           filter_chunk<kMask>(v, (u32)col0 + (u32)(32 * c), st, p);
@@ -569,10 +645,13 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (kCta == 2) cluster_sync_all();  // the leader's MMAs read the peer's shared memory until the very end
   if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)kTmemCols)
-                 : "memory");
+    if (kCta == 2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)kTmemCols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((u32)kTmemCols) : "memory");
   }
 }
 
@@ -674,21 +753,40 @@ static int make_tmap(CUtensorMap* m, const void* base, long long rows, int D, lo
   return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+template <int kMode, int kCta>
+static int launch_variant(const CUtensorMap& tq, const CUtensorMap& ti, const SelectParams& p, cudaStream_t st,
+                          int num_sms) {
+  auto kern = select_tc_kernel<kMode, kCta>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+  if (e != cudaSuccess) return (int)e;
+  const int n_units = p.n_q_tiles * p.S;
+  int workers = num_sms / kCta;  // persistent CTAs (kCta = 1) or CTA pairs (kCta = 2)
+  if (n_units < workers) workers = n_units;
+  if (const char* g = getenv("CCR_DEBUG_GRID")) { int v = atoi(g) / kCta; if (v > 0 && v < workers) workers = v; }
+  if (workers < 1) workers = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(workers * kCta));
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, tq, ti, p);
+  return (int)e;
+}
+
+// p.n_q_tiles counts 128-row tiles for one-CTA units and 256-row tiles when p.two_cta is set
 int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms) {
   CUtensorMap tq, ti;
   int r = make_tmap(&tq, p.q, p.B, p.D, p.ldq, kQTile);
   if (r) return r;
-  r = make_tmap(&ti, p.items, p.n_items, p.D, p.ldi, kITile);
+  r = make_tmap(&ti, p.items, p.n_items, p.D, p.ldi, p.two_cta ? kITile / 2 : kITile);
   if (r) return r;
-  auto kern = p.dense_out ? select_tc_kernel<2> : (p.mask_cols ? select_tc_kernel<1> : select_tc_kernel<0>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-  if (e != cudaSuccess) return (int)e;
-  int n_units = p.n_q_tiles * p.S;
-  int grid = n_units < num_sms ? n_units : num_sms;
-  if (const char* g = getenv("CCR_DEBUG_GRID")) { int v = atoi(g); if (v > 0 && v < grid) grid = v; }
-  if (grid < 1) grid = 1;
-  kern<<<grid, kTcThreads, kTcSmemBytes, st>>>(tq, ti, p);
-  return (int)cudaGetLastError();
+  if (p.dense_out) return launch_variant<2, 1>(tq, ti, p, st, num_sms);
+  if (p.two_cta) return p.mask_cols ? launch_variant<1, 2>(tq, ti, p, st, num_sms) : launch_variant<0, 2>(tq, ti, p, st, num_sms);
+  return p.mask_cols ? launch_variant<1, 1>(tq, ti, p, st, num_sms) : launch_variant<0, 1>(tq, ti, p, st, num_sms);
 }
 
 }  // namespace ccr
