@@ -35,8 +35,10 @@ template <int kCta> struct TcGeom {
   static constexpr int kItemRows = kITile / kCta;
 };
 constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quadrant, one per column half
-constexpr int kTcThreads = 64 + 32 * kEpiWarps; // warps 0..7 epilogue, warp 8 TMA, warp 9 MMA (the
-                                                // scheduler favours high warp ids: keep the feeders there)
+constexpr int kTcThreads = 384;                 // 3 warpgroups: warps 0..7 selection, warp 8 TMA, warp 9 MMA,
+                                                // warps 10..11 idle (whole warpgroups so that setmaxnreg can
+                                                // move registers from the feeders to the selection warps)
+constexpr int kSelRegs = 216, kFeedRegs = 56;
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 constexpr int kLeadTiles = 16;                  // max lead (item tiles) over the slowest CTA on the same split
 constexpr int kStageKeys = 384;                 // candidate buffers up to this size are pruned in smem
@@ -418,7 +420,10 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   tc_fence_after();
   const u32 tmem_base = sh->tmem_base;
 
-  if (warp == kTmaWarp) {
+  if (warp >= kEpiWarps) {
+   // ---- feeder warpgroup: give registers away, then TMA producer / MMA issuer / idle ----
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFeedRegs));
+   if (warp == kTmaWarp) {
     // ================= TMA producer =================
     if (lane == 0) {
       int stage = 0; u32 phase = 0;
@@ -510,7 +515,11 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         }
       }
     }
-  } else if (kMode == 2) {
+   }
+  } else {
+   // ---- selection warpgroups: take the registers the feeders released ----
+   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSelRegs));
+   if (kMode == 2) {
     // ===== store epilogue: thread == query row, writes its 128 columns of the tile as fp32 =====
     const int quad = warp & 3, half = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
@@ -593,31 +602,28 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const u32 taddr0 = tmem_base + ((u32)(quad * 32) << 16) + (u32)(acc * kITile + half * 128);
         const long long col0 = t * kITile + half * 128;
         const bool ragged = col0 + 128 > p.n_items;
-        u32 v[32], w[32];
+        // all 128 columns of this half go to registers first, the accumulator is handed back to the
+        // MMA warp (of the leader CTA when two CTAs share the MMA) immediately, and only then is
+        // anything filtered: the MMA never waits for selection work, only for these four loads
+        u32 v[32], w1[32], w2[32], w3[32];
         tmem_ld_32x32b_x32(taddr0, v);
+        tmem_ld_32x32b_x32(taddr0 + 32u, w1);
+        tmem_ld_32x32b_x32(taddr0 + 64u, w2);
+        tmem_ld_32x32b_x32(taddr0 + 96u, w3);
         tmem_ld_wait();
-        // one filter call site: chunk c is filtered from v while chunk c+1 streams into w
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
+          else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+        }
+        // one filter call site (instruction-cache footprint): the chunks rotate through v
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          if (c < 3) {
-            tmem_ld_32x32b_x32(taddr0 + (u32)(32 * (c + 1)), w);
-          } else {
-            // every column of this half is in registers: hand the accumulator back to the MMA warp
-            // (of the leader CTA when two CTAs share the MMA)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
-              else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
-            }
-          }
           if (ragged) clamp_ragged(v, col0 + 32 * c, p.n_items);
           filter_chunk<kMask>(v, (u32)col0 + (u32)(32 * c), st, p);
-          if (c < 3) {
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = w[j];
-          }
+          for (int j = 0; j < 32; ++j) { v[j] = w1[j]; w1[j] = w2[j]; w2[j] = w3[j]; }
         }
         if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug);
         if ((p.debug & 128) && blockIdx.x == 0 && ew == 0 && lane == 0) {
@@ -641,6 +647,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                  (t_end - t_start) / 1000ull);
       }
     }
+   }
   }
 
   tc_fence_before();
