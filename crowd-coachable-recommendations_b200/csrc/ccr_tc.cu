@@ -617,13 +617,17 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
           else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
         }
-        // one filter call site (instruction-cache footprint): the chunks rotate through v
+        // two filter call sites (instruction-cache footprint vs register moves): chunks 0,1 are
+        // filtered from v,w1; then chunks 2,3 move into those registers and take the same code
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (ragged) clamp_ragged(v, col0 + 32 * c, p.n_items);
+        for (int c = 0; c < 4; c += 2) {
+          if (ragged) { clamp_ragged(v, col0 + 32 * c, p.n_items); clamp_ragged(w1, col0 + 32 * c + 32, p.n_items); }
           filter_chunk<kMask>(v, (u32)col0 + (u32)(32 * c), st, p);
+          filter_chunk<kMask>(w1, (u32)col0 + (u32)(32 * c + 32), st, p);
+          if (c == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = w1[j]; w1[j] = w2[j]; w2[j] = w3[j]; }
+            for (int j = 0; j < 32; ++j) { v[j] = w2[j]; w1[j] = w3[j]; }
+          }
         }
         if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug);
         if ((p.debug & 128) && blockIdx.x == 0 && ew == 0 && lane == 0) {
