@@ -524,11 +524,11 @@ __global__ void __launch_bounds__(256) ingest_kernel(const SrcT* __restrict__ sr
     for (int d = lane; d < D; d += 32) { float v = (float)s[d]; ss = fmaf(v, v, ss); }
 #pragma unroll
     for (int off = 16; off; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
-    scale = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+    scale = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize: x / max(||x||, eps) -- a true division, like torch
   }
   __nv_bfloat16* o = dst + row * ld_dst;
   for (int d = lane; d < ld_dst; d += 32) {
-    float v = d < D ? (float)s[d] * scale : 0.f;
+    float v = d < D ? (normalize ? (float)s[d] / scale : (float)s[d]) : 0.f;
     o[d] = __float2bfloat16_rn(v);
   }
 }
