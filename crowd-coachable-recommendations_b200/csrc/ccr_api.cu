@@ -53,6 +53,7 @@ struct Plan {
   long long seed_ld;     // row pitch of the sampled score matrix (floats)
   size_t off_seed;
   size_t off_progress;
+  size_t off_qpad;       // zero-padded copy of a short query batch (B < 128): every TMA box in bounds
   size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, off_gtau, off_gq, total;
 };
 
@@ -106,6 +107,10 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     }
     pl->halves = 2;
     pl->C = cand_capacity(pl->k_keep, 128);
+    if (const char* cm = getenv("CCR_CAP_MULT")) {  // experiment knob: larger candidate buffers, fewer prunes
+      int m = atoi(cm);
+      if (m >= 1 && m <= 16) pl->C *= m;
+    }
     {
       // streams of one row that run in the first wave; use half of them for the bound so a few
       // late streams do not hold it back
@@ -147,6 +152,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   pl->off_gtau = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(u32), 256);
   pl->off_gq = off;     off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(u32), 256);
   pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
+  pl->off_qpad = off;     off = align_up(off + (size_t)kQTile * 4096 * sizeof(__nv_bfloat16), 256);
   pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
   if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !getenv("CCR_NO_SEED")) {
     // strided sample of max(N/256, 64k) items (4096..131072, <= N/8), capped so the fp32 score matrix
@@ -260,7 +266,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   if (e != cudaSuccess) return fail(CCR_ECUDA, "memset status: %s", cudaGetErrorString(e));
 
   SelectParams sp;
-  sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B;
+  sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B; sp.q_rows = (int)B;
   sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
   sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles; sp.two_cta = pl.two_cta;
   sp.mask_indptr = has_mask ? (const long long*)mask_indptr : nullptr;
@@ -301,6 +307,16 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     if (lr0) return fail(CCR_ECUDA, "seed select launch failed: %s", cudaGetErrorString((cudaError_t)lr0));
   }
 
+  if (pl.algo == CCR_ALGO_TCGEN05 && B < kQTile && n_items > 0 && !getenv("CCR_NO_QPAD")) {
+    // short batch: stage the queries in a zero-padded [128, D] block so that no TMA box of the
+    // query operand is out of bounds (measurably faster than hardware zero-fill of 120+ rows)
+    __nv_bfloat16* qp = (__nv_bfloat16*)(ws + pl.off_qpad);
+    e = cudaMemsetAsync(qp, 0, (size_t)kQTile * D * sizeof(__nv_bfloat16), st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(qp, (size_t)D * 2, q, (size_t)ldq * 2, (size_t)D * 2, (size_t)B, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(CCR_ECUDA, "query padding: %s", cudaGetErrorString(e));
+    sp.q = qp; sp.ldq = D; sp.q_rows = kQTile;
+  }
   int lr = 0;
   if (n_items == 0) {
     e = cudaMemsetAsync(sp.counts, 0, (size_t)pl.rows_pad * pl.S * pl.halves * sizeof(int), st);

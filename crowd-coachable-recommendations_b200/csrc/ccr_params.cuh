@@ -11,6 +11,7 @@ struct SelectParams {
   const __nv_bfloat16* q;
   long long ldq;
   int B;
+  int q_rows;     // rows the query tensor map may address (>= B; > B when the caller padded q)
   const __nv_bfloat16* items;
   long long ldi;
   long long n_items;

@@ -791,7 +791,7 @@ static int launch_variant(const CUtensorMap& tq, const CUtensorMap& ti, const Se
 // p.n_q_tiles counts 128-row tiles for one-CTA units and 256-row tiles when p.two_cta is set
 int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms) {
   CUtensorMap tq, ti;
-  int r = make_tmap(&tq, p.q, p.B, p.D, p.ldq, kQTile);
+  int r = make_tmap(&tq, p.q, p.q_rows > p.B ? p.q_rows : p.B, p.D, p.ldq, kQTile);
   if (r) return r;
   r = make_tmap(&ti, p.items, p.n_items, p.D, p.ldi, p.two_cta ? kITile / 2 : kITile);
   if (r) return r;
