@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libccr_b200.so")
+LIB_PATH = os.environ.get("CCR_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libccr_b200.so")
 
 MASK_NONE, MASK_SET, MASK_ADD = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
