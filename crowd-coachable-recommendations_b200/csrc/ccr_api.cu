@@ -396,4 +396,95 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
   return CCR_OK;
 }
 
+// ---- BM25 (lexical sibling of the dense path) ----
+static void bm25_plan(long long Bq, long long N, int k, int* S, int* C, size_t* off_counts, size_t* total) {
+  const int sms = device_sm_count();
+  const long long rows = Bq > 0 ? Bq : 1;
+  long long s = (2LL * sms + rows - 1) / rows;  // two 512-thread blocks per SM
+  const long long chunks = (N + kBmChunk - 1) / kBmChunk;
+  if (s > chunks) s = chunks;
+  if (s > 1024) s = 1024;  // finalize: kFinMaxStreams
+  if (s < 1) s = 1;
+  *S = (int)s;
+  *C = cand_capacity(k, kBmSlack);
+  const size_t off = align_up((size_t)rows * s * (*C) * sizeof(u64), 256);
+  *off_counts = off;
+  *total = align_up(off + (size_t)rows * s * sizeof(int), 256);
+}
+
+int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
+                           const double* idf, const double* doc_norm, double k1, int64_t n_terms, int64_t nnz,
+                           double* post_val, void* stream) {
+  if (n_terms < 0 || nnz < 0) return fail(CCR_EINVAL, "bad bm25 index shape");
+  if (nnz == 0) return CCR_OK;
+  if (!post_indptr || !post_docs || !post_tf || !idf || !doc_norm || !post_val) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_bm25_impacts((const long long*)post_indptr, post_docs, post_tf, idf, doc_norm, k1 + 1.0, n_terms,
+                               nnz, post_val, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "bm25 impacts launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+size_t ccr_bm25_topk_workspace_bytes(int64_t Bq, int64_t n_docs, int k) {
+  if (Bq < 0 || n_docs < 0 || k < 1 || k > CCR_MAX_K) return 0;
+  int S, C; size_t oc, tot;
+  bm25_plan(Bq, n_docs, k, &S, &C, &oc, &tot);
+  return tot;
+}
+
+static int bm25_check(const int64_t* post_indptr, const int64_t* q_indptr, const int32_t* q_terms, int64_t Bq,
+                      int64_t n_docs, int64_t max_query_terms) {
+  if (Bq < 0 || n_docs < 0) return fail(CCR_EINVAL, "bad bm25 shape");
+  if (Bq > 65535) return fail(CCR_EUNSUPPORTED, "bm25: more than 65535 queries per call");
+  if (n_docs > (1LL << 31) - 512) return fail(CCR_EUNSUPPORTED, "n_docs must be < 2^31");
+  if (max_query_terms < 0 || max_query_terms > kBmMaxTerms)
+    return fail(CCR_EUNSUPPORTED, "bm25: %lld distinct terms in one query (limit %d)", (long long)max_query_terms,
+                kBmMaxTerms);
+  if (Bq > 0 && (!q_indptr || (max_query_terms > 0 && (!q_terms || !post_indptr))))
+    return fail(CCR_EINVAL, "null pointer");
+  return CCR_OK;
+}
+
+int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                  const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                  int64_t n_docs, int k, float* out_scores, int64_t* out_ids, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  int rc = bm25_check(post_indptr, q_indptr, q_terms, Bq, n_docs, max_query_terms);
+  if (rc) return rc;
+  if (k < 1 || k > CCR_MAX_K) return fail(CCR_EUNSUPPORTED, "k=%d outside [1,%d]", k, CCR_MAX_K);
+  if (k > n_docs) return fail(CCR_EK_RANGE, "selected index k out of range (k=%d > n=%lld)", k, (long long)n_docs);
+  if (Bq == 0) return CCR_OK;
+  if (!out_scores || !out_ids) return fail(CCR_EINVAL, "null pointer");
+  int S, C; size_t oc, tot;
+  bm25_plan(Bq, n_docs, k, &S, &C, &oc, &tot);
+  if (!workspace || workspace_bytes < tot) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, tot);
+  unsigned char* ws = (unsigned char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  int lr = launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
+                            Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
+  if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  FinalizeParams fp;
+  fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
+  fp.g_tau = nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
+  fp.id_offset = 0; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
+  lr = launch_finalize(fp, st);
+  if (lr) return fail(CCR_ECUDA, "finalize launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                        const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                        int64_t n_docs, double* scores, int64_t ld, void* stream) {
+  int rc = bm25_check(post_indptr, q_indptr, q_terms, Bq, n_docs, max_query_terms);
+  if (rc) return rc;
+  if (ld < n_docs) return fail(CCR_EINVAL, "ld < n_docs");
+  if (Bq == 0 || n_docs == 0) return CCR_OK;
+  if (!scores) return fail(CCR_EINVAL, "null pointer");
+  int S, C; size_t oc, tot;
+  bm25_plan(Bq, n_docs, 1, &S, &C, &oc, &tot);
+  int lr = launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
+                            Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "bm25 scores launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
 }  // extern "C"

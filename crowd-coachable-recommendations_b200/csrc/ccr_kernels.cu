@@ -581,4 +581,159 @@ int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const _
   return (int)cudaGetLastError();
 }
 
+// =======================================================================================
+// BM25 (lexical sibling of the dense path; reference: scripts/bm_25.py:27-45 scored per query by
+// ranking_bm25, scripts/ms_marco_eval.py:165-186, which full-sorts N scores for 1001 outputs).
+//   bm25_impacts_kernel : at fit time, per posting (term t, doc d, tf):
+//                           val = ((tf * idf_t) * (k1 + 1)) * (1 / (tf + norm[d]))  (float64; scipy
+//                         evaluates sparse / dense as a multiplication by the reciprocal)
+//                         -- the reference's per-query arithmetic does not depend on the query, so
+//                         it is done once; a query then only sums its terms' posting values.
+//   bm25_topk_kernel    : block = (doc split, query).  The split is walked in chunks of kBmChunk
+//                         docs whose float64 score accumulators live in shared memory; the query's
+//                         terms are applied one after the other (fixed order -> deterministic sums),
+//                         each by streaming the term's postings from a per-term cursor until the
+//                         chunk's end (postings are doc-sorted, so no searches in the loop).  The
+//                         finished chunk is either ranked -- as float32, like the reference's
+//                         torch.Tensor(solution).sort -- through the same candidate / prune /
+//                         finalize protocol as the dense kernels (the N-vector never reaches HBM),
+//                         or stored (BM25.transform drop-in).
+// =======================================================================================
+__global__ void __launch_bounds__(256) bm25_impacts_kernel(const long long* __restrict__ post_indptr,
+                                                           const int* __restrict__ post_docs,
+                                                           const float* __restrict__ post_tf,
+                                                           const double* __restrict__ idf,
+                                                           const double* __restrict__ doc_norm, double k1p1,
+                                                           long long V, long long nnz, double* __restrict__ val) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  long long lo = 0, hi = V;  // term of posting e: largest t with post_indptr[t] <= e
+  while (hi - lo > 1) { const long long mid = (lo + hi) >> 1; if (post_indptr[mid] <= e) lo = mid; else hi = mid; }
+  const double tf = (double)post_tf[e];
+  val[e] = ((tf * idf[lo]) * k1p1) * (1.0 / (tf + doc_norm[post_docs[e]]));
+}
+
+int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,
+                        const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
+                        cudaStream_t st) {
+  if (nnz <= 0) return 0;
+  bm25_impacts_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(post_indptr, post_docs, post_tf, idf, doc_norm,
+                                                                    k1p1, V, nnz, val);
+  return (int)cudaGetLastError();
+}
+
+constexpr int kBmThreads = 512;
+constexpr int kBmScan = kBmSlack;  // accumulators ranked between two prune checks
+
+// dynamic shared memory: double acc[kBmChunk]; long long cur[kBmMaxTerms], pend[kBmMaxTerms]; int nxt[kBmMaxTerms]
+constexpr size_t kBmSmem = (size_t)kBmChunk * 8 + (size_t)kBmMaxTerms * (8 + 8 + 4);
+
+__global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* __restrict__ post_indptr,
+                                                               const int* __restrict__ post_docs,
+                                                               const double* __restrict__ post_val,
+                                                               const long long* __restrict__ q_indptr,
+                                                               const int* __restrict__ q_terms, long long N, int k,
+                                                               int C, int S, u64* cand, int* counts,
+                                                               double* dense_out, long long ld_out) {
+  extern __shared__ __align__(16) unsigned char bm_smem[];
+  double* acc = reinterpret_cast<double*>(bm_smem);
+  long long* cur = reinterpret_cast<long long*>(acc + kBmChunk);
+  long long* pend = cur + kBmMaxTerms;
+  int* nxt = reinterpret_cast<int*>(pend + kBmMaxTerms);
+  __shared__ int s_cnt;
+  __shared__ float s_tau_f;
+  __shared__ u64 s_tau_key;
+  __shared__ u32 s_hist[256];
+
+  const int tid = threadIdx.x, split = blockIdx.x;
+  const long long row = blockIdx.y;
+  const long long n_chunks = (N + kBmChunk - 1) / kBmChunk;
+  const long long per = (n_chunks + S - 1) / S;
+  const long long d0 = (long long)split * per * kBmChunk;
+  long long d1 = d0 + per * kBmChunk;
+  if (d1 > N) d1 = N;
+  const long long tb = q_indptr[row];
+  const int T = (int)(q_indptr[row + 1] - tb);
+  u64* buf = cand ? cand + ((long long)row * S + split) * C : nullptr;
+
+  // per-term cursor = first posting with doc >= d0 (one binary search per block and term)
+  for (int t = tid; t < T; t += kBmThreads) {
+    const int term = q_terms[tb + t];
+    long long lo = post_indptr[term];
+    const long long end = post_indptr[term + 1];
+    long long hi = end;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)post_docs[mid] < d0) lo = mid + 1; else hi = mid; }
+    cur[t] = lo;
+    pend[t] = end;
+    nxt[t] = lo < end ? post_docs[lo] : 0x7fffffff;
+  }
+  if (tid == 0) { s_cnt = 0; s_tau_f = -INFINITY; s_tau_key = 0ull; }
+  __syncthreads();
+
+  for (long long c0 = d0; c0 < d1; c0 += kBmChunk) {
+    const long long c1 = c0 + kBmChunk < d1 ? c0 + kBmChunk : d1;
+    const int len = (int)(c1 - c0);
+    for (int j = tid; j < kBmChunk; j += kBmThreads) acc[j] = 0.0;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+      if ((long long)nxt[t] >= c1) continue;  // uniform: shared-memory value
+      long long e = cur[t];
+      const long long end = pend[t];
+      while (true) {  // a doc occurs at most once per term: no conflicts inside an iteration
+        const long long i = e + tid;
+        const int doc = i < end ? post_docs[i] : 0x7fffffff;
+        const bool in = (long long)doc < c1;
+        if (in) acc[doc - (int)c0] += post_val[i];
+        const int n_in = __syncthreads_count(in);
+        if (n_in < kBmThreads) {
+          if (tid == n_in) { cur[t] = e + n_in; nxt[t] = doc; }  // first posting beyond the chunk
+          break;
+        }
+        e += kBmThreads;
+      }
+    }
+    __syncthreads();
+    if (dense_out) {
+      double* o = dense_out + row * ld_out + c0;
+      for (int j = tid; j < len; j += kBmThreads) o[j] = acc[j];
+    } else {
+      for (int base = 0; base < len; base += kBmScan) {
+#pragma unroll
+        for (int u = 0; u < kBmScan / kBmThreads; ++u) {
+          const int j = base + u * kBmThreads + tid;
+          if (j < len) {
+            const float sc = (float)acc[j];
+            if (sc >= s_tau_f) {
+              const u64 key = make_key(sc, (u32)(c0 + j));
+              if (key > s_tau_key) buf[atomicAdd(&s_cnt, 1)] = key;
+            }
+          }
+        }
+        __syncthreads();
+        if (s_cnt > C - kBmScan) {  // uniform: read after the barrier
+          if (tid < 32) {
+            const u64 pivot = warp_prune(buf, s_cnt, k, smem_addr(s_hist), 0u);
+            if (tid == 0) { s_cnt = k; s_tau_key = pivot; s_tau_f = key_score(pivot); }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    __syncthreads();
+  }
+  if (counts && tid == 0) counts[(long long)row * S + split] = s_cnt;
+}
+
+int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const double* post_val,
+                     const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
+                     u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st) {
+  if (Bq <= 0 || N <= 0) return 0;
+  cudaError_t e = cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmSmem);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid((unsigned)S, (unsigned)Bq);
+  bm25_topk_kernel<<<grid, kBmThreads, kBmSmem, st>>>(post_indptr, post_docs, post_val, q_indptr, q_terms, N, k, C, S,
+                                                     cand, counts, dense_out, ld_out);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace ccr

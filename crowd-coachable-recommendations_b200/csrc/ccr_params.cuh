@@ -101,4 +101,15 @@ int launch_normalize_bf16(const __nv_bfloat16* src, long long n, int D, long lon
 int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const __nv_bfloat16* items,
                      long long n, long long ldi, int D, float* out, long long ld_out, cudaStream_t st);
 
+// BM25 (ccr_kernels.cu)
+constexpr int kBmChunk = 8192;     // docs per shared-memory accumulator pass (64 KB of float64)
+constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query
+constexpr int kBmSlack = 1024;     // accumulators ranked between two prune checks
+int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,
+                        const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
+                        cudaStream_t st);
+int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const double* post_val,
+                     const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
+                     u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st);
+
 }  // namespace ccr

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CCR_ABI_VERSION 2
+#define CCR_ABI_VERSION 3
 
 /* error codes */
 #define CCR_OK 0
@@ -132,6 +132,44 @@ int ccr_normalize_rows_bf16(const void* src, int64_t n, int D, int64_t ld_src,
  */
 int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
                         int64_t ldi, int D, float* out, int64_t ld_out, void* stream);
+
+/*
+ * BM25 -- the lexical sibling of the dense path.  Replaces BM25.transform (scripts/bm_25.py:27-45)
+ * and the per-query loop of ranking_bm25 (scripts/ms_marco_eval.py:165-186: one scipy transform,
+ * one FULL sort of n_docs float32 scores and a [0:1001] slice per query).
+ *
+ * Index, resident on the device (CSC of the doc-term count matrix the reference caches,
+ * bm_25.py:22-25):  post_indptr int64[n_terms+1], post_docs int32[nnz] ascending inside a term,
+ * post_tf float32[nnz].
+ *
+ * ccr_bm25_build_impacts (once per fit / cache): per posting of term t in doc d
+ *     post_val = ((tf * idf[t]) * (k1 + 1)) * (1 / (tf + doc_norm[d]))      float64, bm_25.py:39-45
+ * (scipy evaluates the reference's sparse / dense division as a multiplication by the reciprocal)
+ * with idf[t] = log(n/df_t) (sklearn idf_ - 1) and doc_norm[d] = k1 * (1 - b + b * len_d / avdl)
+ * supplied by the host.  The expression does not depend on the query, so it is hoisted out of it.
+ *
+ * Queries: CSR of DISTINCT vocabulary term ids (q_indptr int64[Bq+1], q_terms int32; the
+ * reference uses q.indices only, bm_25.py:38, so query term counts do not matter);
+ * max_query_terms = longest row (<= 512).  score[q, d] = sum of post_val over the query's terms
+ * present in d, summed in q_terms order in float64.
+ *
+ * ccr_bm25_topk: per query the k best docs RANKED AS FLOAT32 (the reference sorts
+ * torch.Tensor(solution), ms_marco_eval.py:179-181), descending, ties -> lowest doc position
+ * (reference: unspecified); out_scores float32 [Bq,k], out_ids int64 [Bq,k].  The n_docs-long
+ * score vector only ever exists chunk-wise in shared memory.  k > n_docs -> CCR_EK_RANGE.
+ * ccr_bm25_scores_f64: the dense float64 score rows themselves (BM25.transform drop-in).
+ */
+int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
+                           const double* idf, const double* doc_norm, double k1, int64_t n_terms, int64_t nnz,
+                           double* post_val, void* stream);
+size_t ccr_bm25_topk_workspace_bytes(int64_t Bq, int64_t n_docs, int k);
+int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                  const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                  int64_t n_docs, int k, float* out_scores, int64_t* out_ids, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                        const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                        int64_t n_docs, double* scores, int64_t ld, void* stream);
 
 /* Which kernel ccr_score_topk_bf16 picks under CCR_ALGO_AUTO: CCR_ALGO_SIMT or CCR_ALGO_TCGEN05. */
 int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k);

@@ -15,6 +15,8 @@ What is restated here (reference paths relative to /root/reference):
 * ``assign_topk_ref``          <- src/rime_lite/util/__init__.py:117-152 (``_assign_topk``)
 * ``argsort_ref``              <- src/rime_lite/util/__init__.py:158-184 (``_argsort``)
 * ``transform_scores_ref``     <- src/ccrec/models/bbpr.py:528-545 (tile loop of ``BertBPR.transform``)
+* ``BM25Ref``                  <- scripts/bm_25.py:9-45 (``BM25.fit/cache/transform``)
+* ``ranking_bm25_ref``         <- scripts/ms_marco_eval.py:165-186 (``ranking_bm25``)
 
 The arithmetic of all of these lives in PyTorch (third-party, version unpinned by the
 reference's setup.py:10-17): ``@``/``mm``, ``F.normalize``, ``Tensor.sort``,
@@ -185,6 +187,80 @@ def transform_scores_ref(all_emb, i_to_ptr, j_to_ptr, batch_size, sim_type):
         scores = cos_sim_ref(user_embedding, ib) if sim_type == "cos" else user_embedding @ ib.T
         out[:, step * batch_size : step * batch_size + ib.shape[0]] = scores
     return out
+
+
+class BM25Ref:
+    """scripts/bm_25.py:9-45 restated on the raw CSC arrays.
+
+    The vocabulary / counting is sklearn's (``TfidfVectorizer(norm=None, smooth_idf=False)``
+    fitted on the corpus, counts from its ``CountVectorizer`` base, bm_25.py:11,23,37); the BM25
+    arithmetic (bm_25.py:39-45) is written out per query term instead of through scipy's
+    sparse/dense operators.  Those operators live in scipy (third party, unpinned by the
+    reference; 1.18.1 in this image, whose evaluation order the goldens capture):
+    ``numer / denom`` with a sparse numerator and a dense denominator is evaluated as
+    ``numer.multiply(1 / denom)`` (scipy/sparse/_base.py ``_divide``) and stays sparse, and
+    ``.sum(1)`` of that sparse matrix adds each row's stored entries in column order.  So for a
+    query with distinct vocabulary terms t_1 < ... < t_T
+
+        score[d] = sum_j  ((tf_jd * idf_j) * (k1 + 1)) * (1 / (tf_jd + k1 * (1 - b + b * len_d / avdl)))
+
+    over the terms present in d, added left to right in float64.
+    """
+
+    def __init__(self, b=0.75, k1=1.6):
+        from sklearn.feature_extraction.text import TfidfVectorizer
+
+        self.vectorizer = TfidfVectorizer(norm=None, smooth_idf=False)
+        self.b, self.k1 = b, k1
+
+    def counts(self, texts):
+        from sklearn.feature_extraction.text import CountVectorizer
+
+        return CountVectorizer.transform(self.vectorizer, texts)
+
+    def fit(self, X):
+        self.vectorizer.fit(X)
+        self.cache(X)
+        self.avdl = self.doc_len.mean()
+        return self
+
+    def cache(self, X):
+        self.csc = self.counts(X).tocsc()
+        self.csc.sort_indices()
+        self.doc_len = np.asarray(self.csc.sum(1)).ravel()
+        return self
+
+    def query_terms(self, q):
+        row = self.counts([q])
+        return row.indices  # distinct vocabulary ids, ascending (sklearn sorts CSR indices)
+
+    def transform(self, q):
+        terms = self.query_terms(q)
+        n = self.csc.shape[0]
+        norm = self.k1 * (1 - self.b + self.b * self.doc_len / self.avdl)
+        idf = self.vectorizer._tfidf.idf_ - 1.0
+        scores = np.zeros(n, dtype=np.float64)
+        for t in terms:
+            lo, hi = self.csc.indptr[t], self.csc.indptr[t + 1]
+            docs = self.csc.indices[lo:hi]
+            tf = self.csc.data[lo:hi].astype(np.float64)
+            scores[docs] += ((tf * idf[t]) * (self.k1 + 1)) * (1.0 / (tf + norm[docs]))
+        return scores
+
+
+def ranking_bm25_ref(corpus, queries, topn=RANKING_TOPN, stable=True):
+    """scripts/ms_marco_eval.py:165-186: fit on the corpus texts, per query score all docs, cast
+    to float32, sort descending, keep the first 1001.  ``stable`` orders exact ties by corpus
+    position (the reference's sort is unstable; ties are unspecified)."""
+    model = BM25Ref(b=0.75, k1=1.2).fit(list(corpus.values()))
+    corpus_ids = list(corpus.keys())
+    profile = {}
+    for qid, text in queries.items():
+        solution = torch.Tensor(model.transform(text))
+        scores, ordering = solution.sort(descending=True, stable=stable)
+        scores, ordering = scores[0:topn], ordering[0:topn]
+        profile[qid] = dict(zip([corpus_ids[i] for i in ordering], scores.numpy().tolist()))
+    return profile
 
 
 # ----------------------------------------------------------------------------------------

@@ -100,3 +100,45 @@ RIME_CASES = {
     "mask_prior_k1": dict(seed=22, b=40, n=700, d=48, k=1, prior=1e5),
     "mask_prior_k10": dict(seed=23, b=17, n=257, d=64, k=10, prior=1.0),
 }
+
+
+def _zipf_text(rs, vocab, n_words):
+    """Space-separated pseudo words w<i>, i ~ Zipf -> a few very common terms, a long tail."""
+    ids = np.minimum(rs.zipf(1.3, size=n_words) - 1, vocab - 1)
+    return " ".join(f"w{int(i)}" for i in ids)
+
+
+def bm25_case(name):
+    """-> dict(corpus {pid: text}, queries {qid: text}).  Texts are Zipfian pseudo-word
+    sequences (sklearn's default token pattern keeps every ``w<i>`` token); a share of the
+    queries are copies of corpus passages (long queries, >= 8 distinct terms, exercise numpy's
+    pairwise row sum), some contain out-of-vocabulary words and repeated words, one is empty."""
+    spec = BM25_CASES[name]
+    rs = np.random.RandomState(spec["seed"])
+    n, q, vocab = spec["n"], spec["q"], spec["vocab"]
+    corpus = {f"p{i}": _zipf_text(rs, vocab, rs.randint(3, spec["doc_len"])) for i in range(n)}
+    pids = list(corpus)
+    queries = {}
+    for i in range(q):
+        kind = i % 4
+        if kind == 0:
+            text = corpus[pids[rs.randint(n)]]
+        elif kind == 1:
+            text = _zipf_text(rs, vocab, rs.randint(1, 6)) + " zzunseen" + str(i)
+        elif kind == 2:
+            w = _zipf_text(rs, vocab, 3)
+            text = w + " " + w
+        else:
+            text = _zipf_text(rs, vocab, rs.randint(2, 12))
+        queries[f"q{i}"] = text
+    if spec.get("empty_query"):
+        queries["q_empty"] = "zzunseen"
+    return dict(corpus=corpus, queries=queries)
+
+
+BM25_CASES = {
+    # fewer than 1001 docs: the whole corpus is returned, zero-score tail in tie order
+    "small_n600": dict(seed=31, n=600, q=12, vocab=300, doc_len=20, empty_query=True),
+    # more than 1001 docs, many docs share no term with the query (zero scores below the cut)
+    "tail_n3000": dict(seed=32, n=3000, q=16, vocab=2000, doc_len=40),
+}

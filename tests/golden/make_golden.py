@@ -10,6 +10,9 @@ tests/golden/cases.py.
 * ranking_<case>.npz : output of scripts/ms_marco_eval.py::ranking (real function, with
   Tensor.cuda()/torch.cuda.synchronize patched to no-ops because this box has no GPU):
   per query the ordered corpus positions and float scores (<=1001 entries).
+* bm25_<case>.npz    : outputs of the real scripts/bm_25.py::BM25 (fit + transform: float64 score
+  vectors of the first queries) and of scripts/ms_marco_eval.py::ranking_bm25 (ordered positions
+  and float scores, <=1001 entries per query).
 * rime_<case>.npz    : outputs of the real rime_lite code: ``_assign_topk`` CSR indices,
   the dense ``as_tensor`` matrix dtype, ``_argsort`` head, ``evaluate_item_rec`` metrics.
 """
@@ -78,7 +81,32 @@ def make_rime():
         print("rime", name, csr.shape, dense.dtype, metrics)
 
 
+def make_bm25():
+    me = _ref_loader.load_ms_marco_eval()
+    import bm_25  # scripts/bm_25.py, on sys.path after load_ms_marco_eval
+
+    for name in cases.BM25_CASES:
+        c = cases.bm25_case(name)
+        prof = me.ranking_bm25(c["corpus"], c["queries"])
+        qids = list(c["queries"].keys())
+        pos = {pid: i for i, pid in enumerate(c["corpus"].keys())}
+        order = np.array([[pos[p] for p in prof[q].keys()] for q in qids], dtype=np.int32)
+        scores = np.array([list(prof[q].values()) for q in qids], dtype=np.float64)
+        model = bm_25.BM25(b=0.75, k1=1.2).fit(list(c["corpus"].values()))
+        dense = np.stack([model.transform(c["queries"][q]) for q in qids[:8]])
+        model16 = bm_25.BM25().fit(list(c["corpus"].values()))  # class defaults b=0.75, k1=1.6
+        dense16 = np.stack([model16.transform(c["queries"][q]) for q in qids[:4]])
+        np.savez_compressed(os.path.join(HERE, f"bm25_{name}.npz"), order=order, scores=scores, dense=dense,
+                            dense_k16=dense16, avdl=np.float64(model.avdl), vocab=len(model.vectorizer.vocabulary_))
+        print("bm25", name, order.shape, dense.shape, "nonzero/row", (dense > 0).sum(1))
+
+
 if __name__ == "__main__":
     assert _ref_loader.reference_available(), "needs /root/reference"
-    make_ranking()
-    make_rime()
+    what = sys.argv[1:] or ["ranking", "rime", "bm25"]
+    if "ranking" in what:
+        make_ranking()
+    if "rime" in what:
+        make_rime()
+    if "bm25" in what:
+        make_bm25()

@@ -109,3 +109,33 @@ def test_check_topk_rule():
     assert O.check_topk(sc, order, ref_scores=sc, ref_ids=order) == []
     with pytest.raises(RuntimeError):
         O.score_topk_ref(torch.zeros(2, 8), torch.zeros(3, 8), 4)
+
+
+@pytest.mark.parametrize("name", list(cases.BM25_CASES))
+def test_bm25_ref_matches_reference(name, golden_dir):
+    """BM25Ref / ranking_bm25_ref vs the real scripts/bm_25.py + ranking_bm25 outputs."""
+    g = np.load(os.path.join(golden_dir, f"bm25_{name}.npz"))
+    c = cases.bm25_case(name)
+    texts = list(c["corpus"].values())
+    qids = list(c["queries"].keys())
+    model = O.BM25Ref(b=0.75, k1=1.2).fit(texts)
+    assert float(model.avdl) == float(g["avdl"]) and len(model.vectorizer.vocabulary_) == int(g["vocab"])
+    dense = np.stack([model.transform(c["queries"][q]) for q in qids[: len(g["dense"])]])
+    np.testing.assert_array_equal(dense, g["dense"])  # same float64 arithmetic -> bit-identical
+    model16 = O.BM25Ref().fit(texts)
+    dense16 = np.stack([model16.transform(c["queries"][q]) for q in qids[: len(g["dense_k16"])]])
+    np.testing.assert_array_equal(dense16, g["dense_k16"])
+    prof = O.ranking_bm25_ref(c["corpus"], c["queries"])
+    pos = {pid: i for i, pid in enumerate(c["corpus"].keys())}
+    order = np.array([[pos[p] for p in prof[q].keys()] for q in qids])
+    scores = np.array([list(prof[q].values()) for q in qids])
+    assert order.shape == g["order"].shape
+    np.testing.assert_array_equal(scores, g["scores"])
+    for b in range(len(qids)):  # ids may differ only inside runs of exactly tied float32 scores
+        if not np.array_equal(order[b], g["order"][b]):
+            diff = order[b] != g["order"][b]
+            for v in np.unique(scores[b][diff]):
+                run = scores[b] == v
+                last = np.nonzero(run)[0][-1] == order.shape[1] - 1  # a run cut by the 1001 slice
+                if not last:
+                    assert set(order[b][run]) == set(g["order"][b][run])
