@@ -59,6 +59,8 @@ struct Plan {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+constexpr long long kTwoCtaMaxB = 2048;  // largest batch served by CTA pairs (see make_plan)
+
 int splits_tc(int nq, long long tiles, int sms) {
   long long smax = tiles < 1 ? 1 : tiles;
   long long s0 = (sms + nq - 1) / nq;
@@ -93,7 +95,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     // limit (B=256: 3.46 vs 4.07 ms); from B=512 up the two variants tie and at B>=4096 the pair is
     // 3-5 % slower with selection on (its MMA waits for 16 selection warps instead of 8) although its
     // GEMM pipeline alone is ~9 % faster.  CCR_2CTA=0/1 overrides.
-    pl->two_cta = (B > kQTile && B <= 3 * kQTile) ? 1 : 0;
+    pl->two_cta = (B > kQTile && B <= kTwoCtaMaxB) ? 1 : 0;
     if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
     const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
     pl->n_q_tiles = (int)((B + unit_rows - 1) / unit_rows);

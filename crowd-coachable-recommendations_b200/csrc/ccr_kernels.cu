@@ -441,7 +441,9 @@ int launch_finalize(const FinalizeParams& p, cudaStream_t st) {
   size_t smem = (size_t)kFinList * 12 + (size_t)(kFinMaxStreams + 2) * 4 + (size_t)P * 12;
   cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
-  finalize_kernel<<<p.B, p.B <= 296 ? kFinMaxThreads : 256, smem, st>>>(p, P);
+  // the gather is latency-bound: few rows -> wide blocks (2 x 1024 threads per SM keep 64 warps of loads
+  // in flight); many rows -> 256-thread blocks fill the SMs on their own
+  finalize_kernel<<<p.B, p.B <= 1536 ? kFinMaxThreads : 256, smem, st>>>(p, P);
   return (int)cudaGetLastError();
 }
 
@@ -623,6 +625,7 @@ int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, cons
 }
 
 constexpr int kBmThreads = 512;
+constexpr int kBmUnroll = 4;      // postings per thread and iteration (memory-level parallelism)
 constexpr int kBmScan = kBmSlack;  // accumulators ranked between two prune checks
 
 // dynamic shared memory: double acc[kBmChunk]; long long cur[kBmMaxTerms], pend[kBmMaxTerms]; int nxt[kBmMaxTerms]
@@ -679,17 +682,43 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
       if ((long long)nxt[t] >= c1) continue;  // uniform: shared-memory value
       long long e = cur[t];
       const long long end = pend[t];
-      while (true) {  // a doc occurs at most once per term: no conflicts inside an iteration
+      bool more = true;
+      {  // first 512 postings on their own: most terms have fewer than that in a chunk
         const long long i = e + tid;
-        const int doc = i < end ? post_docs[i] : 0x7fffffff;
-        const bool in = (long long)doc < c1;
-        if (in) acc[doc - (int)c0] += post_val[i];
+        const int doc = i < end ? __ldg(post_docs + i) : 0x7fffffff;
+        const bool in = (long long)doc < c1;  // doc-sorted: the in-chunk postings are a prefix
+        if (in) acc[doc - (int)c0] += __ldg(post_val + i);
         const int n_in = __syncthreads_count(in);
         if (n_in < kBmThreads) {
           if (tid == n_in) { cur[t] = e + n_in; nxt[t] = doc; }  // first posting beyond the chunk
-          break;
+          more = false;
         }
         e += kBmThreads;
+      }
+      while (more) {  // a doc occurs at most once per term: no conflicts inside an iteration
+        // kBmUnroll x 512 postings per iteration, all loads issued before the first use
+        int doc[kBmUnroll];
+        double v[kBmUnroll];
+#pragma unroll
+        for (int u = 0; u < kBmUnroll; ++u) {
+          const long long i = e + u * kBmThreads + tid;
+          const bool live = i < end;
+          doc[u] = live ? __ldg(post_docs + i) : 0x7fffffff;
+          v[u] = live ? __ldg(post_val + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kBmUnroll; ++u) {
+          if (more) {  // uniform
+            const bool in = (long long)doc[u] < c1;
+            if (in) acc[doc[u] - (int)c0] += v[u];
+            const int n_in = __syncthreads_count(in);
+            if (n_in < kBmThreads) {
+              if (tid == n_in) { cur[t] = e + u * kBmThreads + n_in; nxt[t] = doc[u]; }  // first posting beyond
+              more = false;
+            }
+          }
+        }
+        e += (long long)kBmUnroll * kBmThreads;
       }
     }
     __syncthreads();
