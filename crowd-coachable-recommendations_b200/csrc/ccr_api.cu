@@ -54,7 +54,7 @@ struct Plan {
   size_t off_seed;
   size_t off_progress;
   size_t off_qpad;       // zero-padded copy of a short query batch (B < 128): every TMA box in bounds
-  size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, off_gtau, off_gq, total;
+  size_t off_cand, off_counts, off_ovr_hi, off_ovr_lo, off_status, off_gtau, off_gq, off_hist, off_hpar, total;
 };
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -153,6 +153,8 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
   pl->off_gtau = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(u32), 256);
   pl->off_gq = off;     off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(u32), 256);
+  pl->off_hist = off;   off = align_up(off + (size_t)pl->rows_pad * kHistBins * sizeof(u32), 256);
+  pl->off_hpar = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(uint2), 256);
   pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
   pl->off_qpad = off;     off = align_up(off + (size_t)kQTile * 4096 * sizeof(__nv_bfloat16), 256);
   pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
@@ -281,6 +283,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.g_tau = nullptr; sp.g_q = nullptr; sp.S_row = pl.S * pl.halves; sp.share_j = pl.share_j; sp.share_m = pl.share_m;
   sp.dense_out = nullptr; sp.ld_out = 0;
   sp.progress = nullptr;
+  sp.g_hist = nullptr; sp.g_hpar = nullptr;
   if (pl.algo == CCR_ALGO_TCGEN05 && getenv("CCR_THROTTLE")) {  // opt-in: see DESIGN.md §8
     sp.progress = (int*)(ws + pl.off_progress);
     e = cudaMemsetAsync(sp.progress, 0, (size_t)pl.n_q_tiles * pl.S * sizeof(int), st);
@@ -299,13 +302,17 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
     ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld;
     ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr;
+    // the histogram needs the seed bound as its origin and counts every streamed item, so it is
+    // off in exclude-mask mode (masked items must not be counted)
+    const bool use_hist = sp.mask_cols == nullptr && !getenv("CCR_NO_HIST");
+    if (use_hist) { sp.g_hist = (u32*)(ws + pl.off_hist); sp.g_hpar = (const uint2*)(ws + pl.off_hpar); }
     ss.two_cta = 0; ss.n_q_tiles = pl.rows_pad / kQTile;
     long long tiles = (pl.seed_m + kITile - 1) / kITile;
     ss.S = splits_tc(ss.n_q_tiles, tiles, device_sm_count());
     int lr0 = launch_select_tc(ss, st, device_sm_count());
     if (lr0) return fail(CCR_ECUDA, "seed GEMM launch failed (%d)", lr0);
     lr0 = launch_seed_tau(ss.dense_out, pl.seed_ld, pl.seed_m, (int)B, k, has_mask ? (const long long*)mask_indptr : nullptr,
-                          sp.g_tau, st);
+                          sp.g_tau, use_hist ? (uint2*)(ws + pl.off_hpar) : nullptr, st);
     if (lr0) return fail(CCR_ECUDA, "seed select launch failed: %s", cudaGetErrorString((cudaError_t)lr0));
   }
 

@@ -37,6 +37,14 @@ struct SelectParams {
   int S_row;    // streams per row
   int share_j;
   int share_m;
+  // early threshold sharing through a per-row score histogram (tensor-core kernel, no exclude-mode
+  // mask; null = off).  Row r owns kHistBins counters over ord32(score) buckets of width 2^shift
+  // starting at the row's seed bound (g_hpar[r] = {base, shift + 1}; .y == 0: row disabled).
+  // Every appended candidate group adds its best item to its bucket; whoever finds >= k_row items
+  // counted at or above a bucket's lower edge has a valid lower bound of the row's k-th best --
+  // long before any stream has filled a buffer and pruned.
+  u32* g_hist;        // [rows_pad][kHistBins]
+  const uint2* g_hpar;  // [rows_pad]
   DeviceStatus* status;
   // bounded drift between the CTAs that stream the same item split (keeps their shared item
   // tiles L2-resident so the table is read from HBM once): tiles issued so far, per unit
@@ -88,8 +96,9 @@ struct OverrideParams {
 // launchers (return cudaError_t as int)
 int launch_select_simt(const SelectParams& p, cudaStream_t st);
 int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms);
+constexpr int kHistBins = 128;
 int launch_seed_tau(const float* scores, long long ld, int m, int B, int k, const long long* mask_indptr,
-                    u32* g_tau, cudaStream_t st);
+                    u32* g_tau, uint2* g_hpar, cudaStream_t st);
 int launch_overrides(const OverrideParams& p, cudaStream_t st);
 int launch_finalize(const FinalizeParams& p, cudaStream_t st);
 int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,

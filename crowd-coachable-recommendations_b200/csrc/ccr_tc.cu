@@ -200,6 +200,8 @@ struct SelState {
   int row;         // global query row
   int k_row;       // candidates this row must keep: k (+ the row's mask entries in include mode)
   int stream;      // index of this stream among the row's streams
+  u32* hist;       // the row's score histogram (null: off for this row)
+  u32 hbase, hshift;  // bucket b covers ord32 scores [hbase + (b << hshift), hbase + ((b + 1) << hshift))
   unsigned n_slow, n_prune;  // debug counters (CCR_DEBUG & 4)
 };
 
@@ -225,6 +227,41 @@ __device__ __forceinline__ void append_if_ge(u32 sbits, float tau, u32 nlo0, u64
     buf[cnt] = ((u64)hi << 32) | (u64)(nlo0 - (u32)J);
     cnt += 1;
   }
+}
+
+// One more distinct item of this row scores `s` (>= the row's seed bound): count it in the row's
+// histogram (fire-and-forget RED to L2).
+__device__ __forceinline__ void hist_count(const SelState& st, float s) {
+  const u32 o = ord32(s);
+  if (o >= st.hbase) {
+    u32 b = (o - st.hbase) >> st.hshift;
+    b = b < (u32)(kHistBins - 1) ? b : (u32)(kHistBins - 1);
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(st.hist + b) : "memory");
+  }
+}
+
+// Lower bound of the row's k-th best from its histogram: the lower edge of the highest bucket with
+// at least `need` items counted at or above it (0: not yet).  Counters only grow, so a stale
+// read gives a weaker but still valid bound.  Per-thread code (lane == row): 4 batches of 8
+// independent 16-byte loads from the top bucket down.
+static __device__ __noinline__ u32 hist_bound(const u32* hist, int need, u32 hbase, u32 hshift) {
+  u32 acc = 0u;
+  const uint4* h4 = reinterpret_cast<const uint4*>(hist);
+#pragma unroll 1
+  for (int q4 = kHistBins / 4 - 8; q4 >= 0; q4 -= 8) {
+    uint4 c[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i] = __ldcg(h4 + q4 + i);
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      const int b = (q4 + i) * 4;
+      acc += c[i].w; if (acc >= (u32)need) return hbase + ((u32)(b + 3) << hshift);
+      acc += c[i].z; if (acc >= (u32)need) return hbase + ((u32)(b + 2) << hshift);
+      acc += c[i].y; if (acc >= (u32)need) return hbase + ((u32)(b + 1) << hshift);
+      acc += c[i].x; if (acc >= (u32)need) return hbase + ((u32)b << hshift);
+    }
+  }
+  return 0u;
 }
 
 // Append every score >= tau_f of this 32-column chunk to the row's buffer.  Warp-uniform votes
@@ -254,6 +291,7 @@ __device__ __forceinline__ void filter_chunk(const u32 (&v)[32], u32 col0, SelSt
   }
 #define CCR_GROUP(G)                                                                             \
   if (__any_sync(0xffffffffu, m8[G] >= st.tau_f)) {                                              \
+    if (!kMask && st.hist && m8[G] >= st.tau_f) hist_count(st, m8[G]);                           \
     CCR_APPEND(G * 8 + 0) CCR_APPEND(G * 8 + 1) CCR_APPEND(G * 8 + 2) CCR_APPEND(G * 8 + 3)      \
     CCR_APPEND(G * 8 + 4) CCR_APPEND(G * 8 + 5) CCR_APPEND(G * 8 + 6) CCR_APPEND(G * 8 + 7)      \
   }
@@ -581,6 +619,11 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
       if ((p.debug & 16) && valid_row) st.tau_f = p.debug_tau;
       st.mbeg = 0; st.mend = 0; st.sig = 0ull; st.sig2 = 0ull;
       st.row = row; st.stream = u * 2 + half;
+      st.hist = nullptr; st.hbase = 0u; st.hshift = 0u;
+      if (!kMask && p.g_hist && valid_row) {
+        const uint2 hp = __ldg(p.g_hpar + row);
+        if (hp.y) { st.hist = p.g_hist + (long long)row * kHistBins; st.hbase = hp.x; st.hshift = hp.y - 1u; }
+      }
       st.k_row = k;
       if (!kMask && p.mask_indptr && valid_row) st.k_row = k + (int)(p.mask_indptr[row + 1] - p.mask_indptr[row]);
       if (kMask && valid_row) {
@@ -630,6 +673,17 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           }
         }
         if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug);
+        if (!kMask && p.g_hist) {
+          // refresh the row bound from the histogram at tiles 4, 8, 16, ... 256 and every 256 after
+          const long long ti = t - t0 + 1;
+          if (ti >= 4 && ((ti & (ti - 1)) == 0 || (ti & 255) == 0) && st.hist) {
+            const u32 hb = hist_bound(st.hist, st.k_row, st.hbase, st.hshift);
+            if (hb > ord32(st.tau_f)) {
+              st.tau_f = unord32(hb);
+              atomicMax(p.g_tau + row, hb);
+            }
+          }
+        }
         if ((p.debug & 128) && blockIdx.x == 0 && ew == 0 && lane == 0) {
           const long long ti = t - t0 + 1;
           if ((ti & (ti - 1)) == 0 || t + 1 == t1) {
@@ -674,16 +728,29 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) seed_tau_kernel(const float* __restrict__ scores, long long ld, int m, int B,
                                                        int k, const long long* __restrict__ mask_indptr,
-                                                       u32* __restrict__ g_tau) {
+                                                       u32* __restrict__ g_tau, uint2* __restrict__ g_hpar) {
   __shared__ u32 hist[256];
-  __shared__ u32 s_d, s_need;
+  __shared__ u32 s_d, s_need, s_max;
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   long long h = mask_indptr ? (mask_indptr[row + 1] - mask_indptr[row]) : 0;
   long long kth = (long long)k + h;
-  if (kth > m) return;  // no bound for this row
+  if (kth > m) return;  // no bound for this row (its histogram stays disabled: g_hpar zeroed)
   const float* r = scores + (long long)row * ld;
   u32 prefix = 0, pmask = 0;
   int need = (int)kth;
+  if (g_hpar) {  // best finite sampled score: the upper end of the row's histogram range
+    if (tid == 0) s_max = 0u;
+    __syncthreads();
+    u32 mx = 0u;
+    for (int i = tid; i < m; i += 256) {
+      const u32 o = ord32(r[i]);
+      if (o <= 0xFF7FFFFFu && o > mx) mx = o;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) { const u32 a = __shfl_xor_sync(0xffffffffu, mx, off); mx = a > mx ? a : mx; }
+    if (lane == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+  }
   for (int shift = 24; shift >= 0; shift -= 8) {
     hist[tid] = 0;
     __syncthreads();
@@ -721,13 +788,24 @@ __global__ void __launch_bounds__(256) seed_tau_kernel(const float* __restrict__
     need = (int)s_need;
     __syncthreads();
   }
-  if (tid == 0 && prefix >= 0x00800000u && prefix <= 0xFF7FFFFFu) g_tau[row] = prefix;  // finite scores only
+  if (tid == 0 && prefix >= 0x00800000u && prefix <= 0xFF7FFFFFu) {  // finite scores only
+    g_tau[row] = prefix;
+    if (g_hpar && s_max >= prefix) {
+      // kHistBins buckets of width 2^shift from the seed bound to a little beyond the best sampled
+      // score (the final k-th best of a row lies around the sample's best when k ~ N / m)
+      const u32 span = s_max - prefix;
+      const unsigned long long want = (unsigned long long)span + (span >> 3) + 1ull;
+      u32 shift = 0;
+      while (((unsigned long long)kHistBins << shift) < want) ++shift;
+      g_hpar[row] = make_uint2(prefix, shift + 1u);
+    }
+  }
 }
 
 int launch_seed_tau(const float* scores, long long ld, int m, int B, int k, const long long* mask_indptr, u32* g_tau,
-                    cudaStream_t st) {
+                    uint2* g_hpar, cudaStream_t st) {
   if (B <= 0) return 0;
-  seed_tau_kernel<<<B, 256, 0, st>>>(scores, ld, m, B, k, mask_indptr, g_tau);
+  seed_tau_kernel<<<B, 256, 0, st>>>(scores, ld, m, B, k, mask_indptr, g_tau, g_hpar);
   return (int)cudaGetLastError();
 }
 
