@@ -59,7 +59,7 @@ struct Plan {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr long long kTwoCtaMaxB = 2048;  // largest batch served by CTA pairs (see make_plan)
+constexpr long long kTwoCtaMaxB = 1536;  // largest batch served by CTA pairs (see make_plan)
 
 int splits_tc(int nq, long long tiles, int sms) {
   long long smax = tiles < 1 ? 1 : tiles;
@@ -90,12 +90,13 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
                       !getenv("CCR_MASK_EXCLUDE")) ? 1 : 0;
   pl->k_keep = pl->include_mask ? (int)(k + h_max) : k;
   if (algo == CCR_ALGO_TCGEN05) {
-    // CTA pairs (cta_group::2, 256 query rows per unit).  Measured on B200 (8.84M x 768, k=100): the
-    // pair streams each item tile once for 256 queries, which wins where the item stream is the
-    // limit (B=256: 3.46 vs 4.07 ms); from B=512 up the two variants tie and at B>=4096 the pair is
-    // 3-5 % slower with selection on (its MMA waits for 16 selection warps instead of 8) although its
-    // GEMM pipeline alone is ~9 % faster.  CCR_2CTA=0/1 overrides.
-    pl->two_cta = (B > kQTile && B <= kTwoCtaMaxB) ? 1 : 0;
+    // CTA pairs (cta_group::2, 256 query rows per unit) stream each item tile once for 256 queries
+    // and their GEMM pipeline alone is ~9 % faster.  Measured on B200 (8.84M x 768, k=100, same box,
+    // profiles/r01_midbatch_ab.txt): pairs win for 128 < B <= 1024 (B=256: 2.95 vs 3.27 ms, 512: 5.45
+    // vs 5.87, 1024: 11.3 vs 11.6), tie at 2048, and lose from 3072 up (4096: 47.9 vs 45.0 ms; the
+    // leader's MMA waits for 16 selection warps instead of 8).  A pair pads the batch to 256 rows, so
+    // an odd number of 128-row tiles stays on single CTAs (B=384: 4.72 vs 5.48 ms).
+    pl->two_cta = (B > kQTile && B <= kTwoCtaMaxB && ((B + kQTile - 1) / kQTile) % 2 == 0) ? 1 : 0;
     if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
     const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
     pl->n_q_tiles = (int)((B + unit_rows - 1) / unit_rows);

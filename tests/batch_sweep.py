@@ -46,8 +46,9 @@ def run(items, B, k=100, iters=None):
 
 print("| corpus | B | ms/batch | queries/s | bound | frac of roofline |")
 print("|---|---|---|---|---|---|")
-for name, n, batches in (("MS-MARCO 8,841,823", 8841823, [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384]),
-                         ("NQ 2,681,468", 2681468, [128, 512, 3452])):
+only = [int(x) for x in sys.argv[1:]]  # optional: restrict the MS-MARCO sweep to these batch sizes
+for name, n, batches in (("MS-MARCO 8,841,823", 8841823, only or [1, 2, 4, 8, 16, 32, 64, 128, 256, 384, 512, 1024, 2048, 4096, 8192, 16384]),
+                         ("NQ 2,681,468", 2681468, [] if only else [128, 512, 3452])):
     items = table(n)
     for B in batches:
         ms, qps, frac = run(items, B)

@@ -265,3 +265,51 @@ def test_full_corpus_properties(ccr):
         probe = torch.as_tensor(rs.randint(0, N, size=20000), device=dev)
         probe = probe[~torch.isin(probe, i[b]) & ~torch.isin(probe, torch.as_tensor(rows[b], device=dev))]
         assert float((q[b].float() @ items[probe].float().T).max()) <= float(s[b, -1]) + 1e-3
+
+
+# ---- shapes large enough (N >= 2^18) for the threshold-seeding pre-pass and the per-row histogram
+# ---- sharing to be active, checked against the CPU oracle under the north_star tolerance rule
+SEEDED_CASES = [
+    # B, N, D, k, mode, sim, two_cta
+    (200, 300_000, 128, 10, O.MASK_NONE, "dot", "1"),
+    (300, 300_000, 128, 1001, O.MASK_SET, "dot", "0"),
+    (256, 270_000, 64, 100, O.MASK_ADD, "dot", "1"),
+    (130, 400_000, 64, 2048, O.MASK_NONE, "cos", "0"),
+    (5, 300_000, 128, 100, O.MASK_SET, "dot", "0"),
+]
+
+
+@pytest.mark.parametrize("B,N,D,k,mode,sim,two", SEEDED_CASES)
+def test_seeded_histogram_path_matches_oracle(ccr, B, N, D, k, mode, sim, two, monkeypatch):
+    monkeypatch.setenv("CCR_2CTA", two)
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(B + k)
+    P = cases.embeddings(B * 7 + k, N, D, clustered=(sim == "cos"))
+    Q = cases.embeddings(B * 11 + k, B, D, clustered=(sim == "cos"))
+    P[rs.randint(0, N, size=2000)] = P[rs.randint(0, N, size=2000)]  # some exact ties
+    table = ccr.EmbeddingTable.from_tensor(torch.as_tensor(P), device=dev, normalize=(sim == "cos"))
+    mask = _mask(rs, B, N, mode, dev, ccr) if mode != O.MASK_NONE else None
+    s, i, d = table.search(torch.as_tensor(Q), k, mask=mask, algo=2, want_f64=True)
+    torch.cuda.synchronize()
+    rs_, ri_ = O.score_topk_ref(Q, P, k, mask=mask.host if mask else None, mode=mode, sim=sim)
+    errs = O.check_topk(d.cpu().numpy(), i.cpu().numpy(), ref_scores=rs_.numpy(), ref_ids=ri_.numpy(), rtol=RTOL,
+                        atol=2e-3 if sim == "cos" else 1e-4)
+    assert not errs, errs[:3]
+    # and the histogram sharing must not change a single bit of the result
+    monkeypatch.setenv("CCR_NO_HIST", "1")
+    s0, i0, d0 = table.search(torch.as_tensor(Q), k, mask=mask, algo=2, want_f64=True)
+    assert torch.equal(i, i0) and torch.equal(d, d0)
+
+
+def test_seeded_path_degenerate_scores(ccr):
+    """All-zero table at a seeded size: every score ties, positions 0..k-1 must come back; and a
+    table whose rows are all the same vector (one distinct score per query)."""
+    dev = torch.device("cuda:0")
+    N, D, k = 300_000, 64, 7
+    q = torch.randn(150, D, device=dev).to(torch.bfloat16)
+    s, i = ccr.score_topk(q, torch.zeros(N, D, device=dev, dtype=torch.bfloat16), k, algo=2)
+    assert bool((i == torch.arange(k, device=dev)).all()) and float(s.abs().max()) == 0.0
+    row = torch.randn(1, D, device=dev).to(torch.bfloat16)
+    s, i = ccr.score_topk(q, row.expand(N, D).contiguous(), k, algo=2)
+    assert bool((i == torch.arange(k, device=dev)).all())
+    torch.testing.assert_close(s[:, 0], (q.float() @ row.float().T)[:, 0], rtol=1e-4, atol=1e-3)
