@@ -6,6 +6,7 @@ Public surface (mirrors the reference's call sites for this path):
 * ``_assign_topk`` / ``assign_topk``                       <- src/rime_lite/util/__init__.py
 * ``LazyDenseMatrix`` ... ``auto_cast_lazy_score``         <- src/rime_lite/util/score_array.py
 * ``evaluate_item_rec`` / ``evaluate_assigned``            <- src/rime_lite/metrics/__init__.py
+* ``al_rank.rank_step`` / ``build_requests`` ...           <- scripts/al_0_rank.py:107-218
 * ``BM25`` / ``ranking_bm25``                             <- scripts/bm_25.py, scripts/ms_marco_eval.py:165-186
 * ``EmbeddingTable`` / ``ShardedIndex``                    (residency + row-sharding layer)
 * ``score_topk`` / ``merge_topk``                          (thin wrappers of the C ABI)
@@ -37,3 +38,4 @@ from .ranking import (  # noqa: F401
 )
 from .dist import ShardedIndex, shard_bounds  # noqa: F401
 from .bm25 import BM25, ranking_bm25  # noqa: F401
+from . import al_rank  # noqa: F401

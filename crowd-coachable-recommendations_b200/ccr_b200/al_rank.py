@@ -1,0 +1,148 @@
+"""Step 0 of the human-in-the-loop cycle with the same inputs and outputs as
+scripts/al_0_rank.py: ``ranking_profile.pt`` (cached per step, :111-127), MRR@{1,5,10,100}
+(:130-133), 4-candidate labelling tasks = dense top-2 + first unseen BM25 hit + random fill
+(:165-182), ``id_track.pt`` / ``request_orig.csv`` / ``request_perm.csv`` (:196-218).
+
+The script itself is module-level code that is not importable at the reference's HEAD (it imports
+``load_corpus`` / ``load_query`` that do not exist) and drags in the encoder; here
+the same step is a function of already-loaded inputs.  Only the ``ranking(...)`` call runs on the
+device (ccr_b200.ranking); everything after it is host bookkeeping whose byte-for-byte output is
+pinned by tests/golden/al0_*.npz (produced by executing the reference's own statements).
+
+Random draws follow the reference exactly: candidates use ``RandomState(STEP)`` with one
+``choice(len(corpus))`` per attempt, the display order uses ``RandomState(REPEAT_SEED)`` with one
+``permutation(4)`` per emitted row.
+"""
+from __future__ import annotations
+
+import os
+import re
+
+import numpy as np
+
+HEADER = ["query", "passage-1", "passage-2", "passage-3", "passage-4", "qid", "pid-1", "pid-2", "pid-3", "pid-4"]
+IMAGE_HEADER = ["img-q", "img-1", "img-2", "img-3", "img-4"]
+_KEEP = re.compile(r"[^a-zA-Z0-9 ,:.;?$!()&\[\]]")
+
+
+def filter_string(text, display_length=None):
+    """Characters the MTurk layout may show, cut to CCREC_DISPLAY_LENGTH (al_0_rank.py:142-144)."""
+    if display_length is None:
+        display_length = int(os.environ["CCREC_DISPLAY_LENGTH"])
+    return _KEEP.sub("", text)[:display_length]
+
+
+def mrr_from_profile(qrels, ranking_profile, k_values=(1, 5, 10, 100)):
+    """MRR@k as al_0_rank.py:130-133 obtains it from BEIR (``EvaluateRetrieval.evaluate_custom(qrels,
+    results, k_values, metric="mrr")`` -- third party, unvendored and unpinned by the reference;
+    its published algorithm: per query the results are ordered by score, the reciprocal rank of the
+    first hit with qrels score > 0 inside the top k is summed, the sum is divided by ``len(qrels)``
+    and rounded to 5 digits)."""
+    k_max = max(k_values)
+    sums = {k: 0.0 for k in k_values}
+    for qid, scored in ranking_profile.items():
+        relevant = {pid for pid, rel in qrels.get(qid, {}).items() if rel > 0}
+        if not relevant:
+            continue
+        top = sorted(scored.items(), key=lambda kv: kv[1], reverse=True)[:k_max]
+        first = next((r for r, (pid, _) in enumerate(top) if pid in relevant), None)
+        if first is not None:
+            for k in k_values:
+                if first < k:
+                    sums[k] += 1.0 / (first + 1)
+    n = max(1, len(qrels))
+    return {f"MRR@{k}": round(sums[k] / n, 5) for k in k_values}
+
+
+def select_candidates(ranks, ranks_bm25, corpus_keys, rng):
+    """Dense top-2, then the best BM25 passage not among them, then random corpus passages until
+    there are four distinct ones (al_0_rank.py:169-182)."""
+    cands = list(ranks[:2])
+    for pid in ranks_bm25:  # normally adds exactly one; more only if the dense list is shorter than 2
+        if len(cands) >= 3:
+            break
+        if pid not in cands:
+            cands.append(pid)
+    while len(cands) < 4:
+        pid = corpus_keys[rng.choice(len(corpus_keys))]
+        if pid not in cands:
+            cands.append(pid)
+    return cands
+
+
+def build_requests(ranking_profile, ranking_profile_bm25, corpus, queries, split_qids, step, landing_image=None):
+    """-> (header, rows, id_track) for the queries of this step's split, in ranking_profile order."""
+    rng = np.random.RandomState(step)
+    corpus_keys = list(corpus.keys())
+    wanted = split_qids if isinstance(split_qids, (set, frozenset)) else set(np.asarray(split_qids).tolist())
+    header = HEADER + (IMAGE_HEADER if landing_image is not None else [])
+    rows, id_track = [], {}
+    for qid, scored in ranking_profile.items():
+        if qid not in wanted:
+            continue
+        cands = select_candidates(list(scored.keys()), ranking_profile_bm25[qid].keys(), corpus_keys, rng)
+        passages = [filter_string(corpus[pid]) for pid in cands]
+        row = [queries[qid], *passages, f"q_{qid}", *(f"p_{pid}" for pid in cands)]
+        if landing_image is not None:
+            row += [landing_image[qid], *(landing_image[pid] for pid in cands)]
+        rows.append(row)
+        id_track[queries[qid]] = f"q_{qid}"
+        id_track.update({text: f"p_{pid}" for pid, text in zip(cands, passages)})
+    return header, rows, id_track
+
+
+def permute_requests(rows, n_repeats, repeat_seed):
+    """n_repeats copies of every task with its four passages (and ids, images) shown in an
+    independently drawn order (al_0_rank.py:204-215)."""
+    rng = np.random.RandomState(repeat_seed)
+    out = []
+    for _ in range(n_repeats):
+        for row in rows:
+            order = rng.permutation(4)
+            shown = [row[0], *(row[1 + i] for i in order), row[5], *(row[6 + i] for i in order)]
+            if len(row) > 10:
+                shown += [row[10], *(row[11 + i] for i in order)]
+            out.append(shown)
+    return out
+
+
+def write_requests(working_dir, header, rows, id_track, n_repeats, repeat_seed):
+    """id_track.pt, request_orig.csv, request_perm.csv exactly as al_0_rank.py:196-218 writes them."""
+    import pandas as pd
+    import torch
+
+    os.makedirs(working_dir, exist_ok=True)
+    torch.save(id_track, os.path.join(working_dir, "id_track.pt"))
+    request_orig = pd.DataFrame(rows, columns=header)
+    request_orig.to_csv(os.path.join(working_dir, "request_orig.csv"), index=False)
+    request_perm = pd.DataFrame(permute_requests(rows, n_repeats, repeat_seed), columns=header)
+    request_perm.to_csv(os.path.join(working_dir, "request_perm.csv"), index=False)
+    return request_orig, request_perm
+
+
+def rank_step(corpus, queries, qrels, embedding_func, results_dir, step, ranking_profile_bm25, qids_split,
+              n_repeats=3, repeat_seed=42, number_of_qid_split_batch=None, block_dict=None, landing_image=None,
+              batch_size=512, device="cuda"):
+    """al_0_rank.py:107-218 as a function: reuse or compute ``data_iteration_{step}/ranking_profile.pt``
+    (the dense retrieval runs through ccr_b200.ranking on the device), report MRR, write the
+    labelling requests.  Returns (ranking_profile, mrr, request_orig, request_perm)."""
+    import torch
+
+    from .ranking import ranking
+
+    working_dir = os.path.join(results_dir, f"data_iteration_{step}")
+    os.makedirs(working_dir, exist_ok=True)
+    profile_path = os.path.join(working_dir, "ranking_profile.pt")
+    if os.path.isfile(profile_path):
+        ranking_profile = torch.load(profile_path)
+    else:
+        ranking_profile = ranking(corpus, queries, embedding_func, batch_size, block_dict, device=device)
+        torch.save(ranking_profile, profile_path)
+    mrr = mrr_from_profile(qrels, ranking_profile, [1, 5, 10, 100])
+    for name, value in mrr.items():
+        print(name, ":", value)
+    split = qids_split[step % (number_of_qid_split_batch or len(qids_split))]
+    header, rows, id_track = build_requests(ranking_profile, ranking_profile_bm25, corpus, queries, split, step,
+                                            landing_image)
+    request_orig, request_perm = write_requests(working_dir, header, rows, id_track, n_repeats, repeat_seed)
+    return ranking_profile, mrr, request_orig, request_perm

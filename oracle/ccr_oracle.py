@@ -17,6 +17,7 @@ What is restated here (reference paths relative to /root/reference):
 * ``transform_scores_ref``     <- src/ccrec/models/bbpr.py:528-545 (tile loop of ``BertBPR.transform``)
 * ``BM25Ref``                  <- scripts/bm_25.py:9-45 (``BM25.fit/cache/transform``)
 * ``ranking_bm25_ref``         <- scripts/ms_marco_eval.py:165-186 (``ranking_bm25``)
+* ``al0_requests_ref``         <- scripts/al_0_rank.py:136-218 (candidates, id_track, request_orig/perm)
 
 The arithmetic of all of these lives in PyTorch (third-party, version unpinned by the
 reference's setup.py:10-17): ``@``/``mm``, ``F.normalize``, ``Tensor.sort``,
@@ -261,6 +262,57 @@ def ranking_bm25_ref(corpus, queries, topn=RANKING_TOPN, stable=True):
         scores, ordering = scores[0:topn], ordering[0:topn]
         profile[qid] = dict(zip([corpus_ids[i] for i in ordering], scores.numpy().tolist()))
     return profile
+
+
+def al0_requests_ref(ranking_profile, ranking_profile_bm25, corpus, queries, qids_split, step,
+                     number_of_qid_split_batch, n_repeats, repeat_seed, landing_image=None, display_length=250):
+    """scripts/al_0_rank.py:136-218 as a function of its inputs.  Returns (header, rows,
+    permuted_rows, id_track); the CSV files are ``pd.DataFrame(rows, columns=header).to_csv(index=False)``.
+
+    :138 ranks_rng = RandomState(STEP); :165-167 only queries of split STEP % n; :169-177 dense
+    top-2 then BM25 passages until three; :179-182 random corpus passages (one ``choice`` per
+    attempt) until four; :184-194 row + id_track; :204-215 N_REPEATS passes, one ``permutation(4)``
+    per row applied to passages, pids and images alike."""
+    import re
+
+    ranks_rng = np.random.RandomState(step)
+    corpus_keys = list(corpus.keys())
+    header = ["query"] + [f"passage-{i}" for i in range(1, 5)] + ["qid"] + [f"pid-{i}" for i in range(1, 5)]
+    if landing_image is not None:
+        header += ["img-q"] + [f"img-{i}" for i in range(1, 5)]
+    split = qids_split[step % number_of_qid_split_batch]
+    rows, id_track = [], {}
+    for qid in ranking_profile:
+        if qid not in split:
+            continue
+        cands = list(ranking_profile[qid].keys())[0:2]
+        for pid in ranking_profile_bm25[qid].keys():
+            if len(cands) == 3:
+                break
+            if pid not in cands:
+                cands.append(pid)
+        while len(cands) < 4:
+            pid = corpus_keys[ranks_rng.choice(len(corpus_keys))]
+            if pid not in cands:
+                cands.append(pid)
+        passages = [re.sub(r"[^a-zA-Z0-9 ,:.;?$!()&\[\]]", "", corpus[pid])[:display_length] for pid in cands]
+        row = [queries[qid]] + passages + [f"q_{qid}"] + [f"p_{c}" for c in cands]
+        if landing_image is not None:
+            row = row + [landing_image[qid]] + [landing_image[c] for c in cands]
+        rows.append(row)
+        id_track[queries[qid]] = f"q_{qid}"
+        for pid, passage in zip(cands, passages):
+            id_track[passage] = f"p_{pid}"
+    rng = np.random.RandomState(repeat_seed)
+    permuted = []
+    for _ in range(n_repeats):
+        for row in rows:
+            ind = rng.permutation(4)
+            out = [row[0]] + [row[1 + i] for i in ind] + [row[5]] + [row[6 + i] for i in ind]
+            if len(row) > 10:
+                out = out + [row[10]] + [row[11 + i] for i in ind]
+            permuted.append(out)
+    return header, rows, permuted, id_track
 
 
 # ----------------------------------------------------------------------------------------

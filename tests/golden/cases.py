@@ -142,3 +142,61 @@ BM25_CASES = {
     # more than 1001 docs, many docs share no term with the query (zero scores below the cut)
     "tail_n3000": dict(seed=32, n=3000, q=16, vocab=2000, doc_len=40),
 }
+
+
+def al0_case(name):
+    """Inputs of scripts/al_0_rank.py:136-218 (the request-building part): corpus / queries with
+    characters the display filter drops, a dense and a BM25 ranking profile per query, the qid
+    splits, STEP / N_REPEATS / REPEAT_SEED and (optionally) the landing-image table."""
+    import pandas as pd
+
+    spec = AL0_CASES[name]
+    rs = np.random.RandomState(spec["seed"])
+    n, q = spec["n"], spec["q"]
+    junk = ["é", "—", "#", "@", "\"", "'", "%", "\n", "/", "*"]
+    keep = list("abcXYZ019 ,:.;?$!()&[]")
+
+    def text(length):
+        chars = [junk[rs.randint(len(junk))] if rs.rand() < 0.15 else keep[rs.randint(len(keep))] for _ in range(length)]
+        return "".join(chars)
+
+    corpus = {f"d{i}": text(rs.randint(5, spec["text_len"])) for i in range(n)}
+    same = spec.get("queries_are_corpus", False)
+    queries = {pid: corpus[pid] for pid in list(corpus)[:q]} if same else {f"{1000 + i}": text(rs.randint(5, 60)) for i in range(q)}
+    pids = np.array(list(corpus))
+    depth = min(n, spec["depth"])
+
+    def profile():
+        out = {}
+        for qid in queries:
+            order = rs.permutation(n)[:depth]
+            scores = np.sort(rs.standard_normal(depth).astype(np.float32))[::-1]
+            out[qid] = dict(zip(pids[order].tolist(), scores.tolist()))
+        return out
+
+    dense, bm25 = profile(), profile()
+    if spec.get("bm25_overlap"):  # BM25's best hits coincide with the dense top-2: the third comes later
+        for qid in queries:
+            head = list(dense[qid])[:2]
+            rest = [p for p in bm25[qid] if p not in head]
+            bm25[qid] = dict(zip(head + rest, sorted(bm25[qid].values(), reverse=True)))
+    qids = list(queries)
+    rs.shuffle(qids)
+    nsplit = spec["splits"]
+    qids_split = [qids[i::nsplit] for i in range(nsplit)]
+    landing = None
+    if spec.get("images"):
+        landing = pd.Series({pid: f"https://img.example/{pid}.jpg" for pid in corpus})
+    return dict(corpus=corpus, queries=queries, ranking_profile=dense, ranking_profile_bm25=bm25,
+                qids_split=qids_split, number_of_qid_split_batch=nsplit, step=spec["step"],
+                n_repeats=spec["n_repeats"], repeat_seed=spec["repeat_seed"], landing_image=landing)
+
+
+AL0_CASES = {
+    "nq_like_step1": dict(seed=51, n=400, q=60, depth=101, text_len=400, splits=4, step=1, n_repeats=3, repeat_seed=42,
+                          bm25_overlap=True),
+    # Prime-Pantry-like: queries are corpus items, images attached, tiny corpus so the random fill
+    # collides with existing candidates (extra RNG draws), step wraps around the splits
+    "pantry_like_step5": dict(seed=52, n=6, q=6, depth=3, text_len=300, splits=4, step=5, n_repeats=2,
+                              repeat_seed=7, queries_are_corpus=True, images=True),
+}

@@ -13,6 +13,11 @@ tests/golden/cases.py.
 * bm25_<case>.npz    : outputs of the real scripts/bm_25.py::BM25 (fit + transform: float64 score
   vectors of the first queries) and of scripts/ms_marco_eval.py::ranking_bm25 (ordered positions
   and float scores, <=1001 entries per query).
+* al0_<case>.npz     : bytes of request_orig.csv / request_perm.csv and the id_track dict written by
+  the request-building statements of scripts/al_0_rank.py ("## creation" to the end of the file,
+  :136-218).  The script is module-level code that cannot be imported (argparse, downloads, an
+  ImportError at :28-34), so exactly those statements are read from the reference file at
+  generation time and executed unmodified in a namespace holding the synthetic inputs.
 * rime_<case>.npz    : outputs of the real rime_lite code: ``_assign_topk`` CSR indices,
   the dense ``as_tensor`` matrix dtype, ``_argsort`` head, ``evaluate_item_rec`` metrics.
 """
@@ -101,12 +106,42 @@ def make_bm25():
         print("bm25", name, order.shape, dense.shape, "nonzero/row", (dense > 0).sum(1))
 
 
+def make_al0():
+    import re
+    import tempfile
+
+    import pandas as pd
+
+    src = open(os.path.join(_ref_loader.REFERENCE_ROOT, "scripts", "al_0_rank.py")).read()
+    creation = src[src.index("## creation"):]
+    os.environ["CCREC_DISPLAY_LENGTH"] = "250"  # al_0_rank.py:13
+    for name in cases.AL0_CASES:
+        c = cases.al0_case(name)
+        with tempfile.TemporaryDirectory() as tmp:
+            ns = dict(np=np, pd=pd, re=re, os=os, torch=torch, STEP=c["step"], corpus=c["corpus"], queries=c["queries"],
+                      ranking_profile=c["ranking_profile"], ranking_profile_bm25=c["ranking_profile_bm25"],
+                      qids_split=c["qids_split"], number_of_qid_split_batch=c["number_of_qid_split_batch"],
+                      landingImage=c["landing_image"], current_working_dir=tmp, N_REPEATS=c["n_repeats"],
+                      REPEAT_SEED=c["repeat_seed"])
+            exec(compile(creation, "al_0_rank.py[creation]", "exec"), ns)
+            orig = open(os.path.join(tmp, "request_orig.csv"), "rb").read()
+            perm = open(os.path.join(tmp, "request_perm.csv"), "rb").read()
+            track = torch.load(os.path.join(tmp, "id_track.pt"))
+        np.savez_compressed(os.path.join(HERE, f"al0_{name}.npz"), request_orig=np.frombuffer(orig, dtype=np.uint8),
+                            request_perm=np.frombuffer(perm, dtype=np.uint8),
+                            id_track_keys=np.array(list(track.keys()), dtype=object).astype(str),
+                            id_track_vals=np.array(list(track.values()), dtype=object).astype(str))
+        print("al0", name, len(orig), len(perm), len(track))
+
+
 if __name__ == "__main__":
     assert _ref_loader.reference_available(), "needs /root/reference"
-    what = sys.argv[1:] or ["ranking", "rime", "bm25"]
+    what = sys.argv[1:] or ["ranking", "rime", "bm25", "al0"]
     if "ranking" in what:
         make_ranking()
     if "rime" in what:
         make_rime()
     if "bm25" in what:
         make_bm25()
+    if "al0" in what:
+        make_al0()

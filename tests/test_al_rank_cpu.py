@@ -1,0 +1,84 @@
+"""al_0_rank request building (scripts/al_0_rank.py:136-218): the oracle restatement and the
+product's host logic (ccr_b200.al_rank) against outputs of the reference's own statements
+(tests/golden/al0_*.npz).  Pure host code: runs without a GPU."""
+import io
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import cases
+from oracle import ccr_oracle as O
+
+
+def _csv(header, rows):
+    buf = io.StringIO()
+    pd.DataFrame(rows, columns=header).to_csv(buf, index=False)
+    return buf.getvalue().encode()
+
+
+@pytest.mark.parametrize("name", list(cases.AL0_CASES))
+def test_oracle_requests_match_reference(name, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"al0_{name}.npz"))
+    c = cases.al0_case(name)
+    header, rows, perm, track = O.al0_requests_ref(
+        c["ranking_profile"], c["ranking_profile_bm25"], c["corpus"], c["queries"], c["qids_split"], c["step"],
+        c["number_of_qid_split_batch"], c["n_repeats"], c["repeat_seed"], c["landing_image"])
+    assert _csv(header, rows) == g["request_orig"].tobytes()
+    assert _csv(header, perm) == g["request_perm"].tobytes()
+    assert list(track.keys()) == g["id_track_keys"].tolist() and list(track.values()) == g["id_track_vals"].tolist()
+
+
+@pytest.mark.parametrize("name", list(cases.AL0_CASES))
+def test_product_requests_match_reference(name, golden_dir, tmp_path, monkeypatch):
+    """Same ranking_profile in -> byte-identical request_orig.csv / request_perm.csv / id_track out."""
+    from ccr_b200 import al_rank
+
+    monkeypatch.setenv("CCREC_DISPLAY_LENGTH", "250")
+    g = np.load(os.path.join(golden_dir, f"al0_{name}.npz"))
+    c = cases.al0_case(name)
+    split = c["qids_split"][c["step"] % c["number_of_qid_split_batch"]]
+    header, rows, track = al_rank.build_requests(c["ranking_profile"], c["ranking_profile_bm25"], c["corpus"],
+                                                 c["queries"], split, c["step"], c["landing_image"])
+    al_rank.write_requests(str(tmp_path), header, rows, track, c["n_repeats"], c["repeat_seed"])
+    assert open(tmp_path / "request_orig.csv", "rb").read() == g["request_orig"].tobytes()
+    assert open(tmp_path / "request_perm.csv", "rb").read() == g["request_perm"].tobytes()
+    saved = torch.load(tmp_path / "id_track.pt")
+    assert list(saved.keys()) == g["id_track_keys"].tolist() and list(saved.values()) == g["id_track_vals"].tolist()
+
+
+def test_rank_step_reuses_cached_profile(tmp_path, monkeypatch):
+    """al_0_rank.py:117-118: an existing ranking_profile.pt is loaded instead of recomputed -- so the
+    whole step runs without touching the device; outputs land in data_iteration_{STEP}/."""
+    from ccr_b200 import al_rank
+
+    monkeypatch.setenv("CCREC_DISPLAY_LENGTH", "250")
+    c = cases.al0_case("nq_like_step1")
+    wd = tmp_path / f"data_iteration_{c['step']}"
+    wd.mkdir()
+    torch.save(c["ranking_profile"], wd / "ranking_profile.pt")
+    qid0 = next(iter(c["queries"]))
+    qrels = {qid0: {next(iter(c["ranking_profile"][qid0])): 1}}
+
+    def boom(_texts):
+        raise AssertionError("embedding_func must not be called when the profile is cached")
+
+    prof, mrr, orig, perm = al_rank.rank_step(c["corpus"], c["queries"], qrels, boom, str(tmp_path), c["step"],
+                                              c["ranking_profile_bm25"], c["qids_split"], c["n_repeats"],
+                                              c["repeat_seed"])
+    assert prof == c["ranking_profile"] and mrr["MRR@1"] == 1.0
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "al0_nq_like_step1.npz"))
+    assert open(wd / "request_perm.csv", "rb").read() == g["request_perm"].tobytes()
+    assert len(perm) == c["n_repeats"] * len(orig)
+
+
+def test_mrr_from_profile_follows_beir_semantics():
+    from ccr_b200 import al_rank
+
+    prof = {"q0": {"a": 3.0, "b": 2.0, "c": 1.0}, "q1": {"a": 0.1, "c": 0.9, "b": 0.5}, "q2": {"a": 1.0}}
+    qrels = {"q0": {"b": 1}, "q1": {"a": 2, "b": 0}, "q2": {"z": 1}, "q3": {"a": 1}}
+    m = al_rank.mrr_from_profile(qrels, prof, (1, 2, 3))
+    # q0: first hit at rank 2; q1: ordered c, b, a -> rank 3; q2: none; divided by len(qrels) = 4
+    assert m == {"MRR@1": 0.0, "MRR@2": round(0.5 / 4, 5), "MRR@3": round((0.5 + 1 / 3) / 4, 5)}

@@ -313,3 +313,36 @@ def test_seeded_path_degenerate_scores(ccr):
     s, i = ccr.score_topk(q, row.expand(N, D).contiguous(), k, algo=2)
     assert bool((i == torch.arange(k, device=dev)).all())
     torch.testing.assert_close(s[:, 0], (q.float() @ row.float().T)[:, 0], rtol=1e-4, atol=1e-3)
+
+
+def test_al0_rank_step_end_to_end(ccr, tmp_path, monkeypatch):
+    """al_0_rank.py:107-218 through ccr_b200.al_rank.rank_step: dense retrieval on the device,
+    ranking_profile.pt written and reused, MRR, and request CSVs byte-identical to the oracle's
+    restatement applied to the same profile."""
+    import io
+
+    import pandas as pd
+
+    monkeypatch.setenv("CCREC_SIM_TYPE", "dot")
+    monkeypatch.setenv("CCREC_DISPLAY_LENGTH", "250")
+    c = cases.ranking_case("dot_n1500")
+    table = cases.TextTable(c["table"])
+    qids = list(c["queries"])
+    bm25 = {q: {p: 1.0 / (r + 1) for r, p in enumerate(list(c["corpus"])[i:i + 50])} for i, q in enumerate(qids)}
+    splits = [qids[0::2], qids[1::2]]
+    want = O.ranking_ref(c["corpus"], c["queries"], cases.TextTable(c["table"]), c["batch_size"], None, sim_type="dot")
+    qrels = {q: {next(iter(want[q])): 1} for q in qids}  # the oracle's best passage is the relevant one
+    prof, mrr, orig, perm = ccr.al_rank.rank_step(c["corpus"], c["queries"], qrels, table, str(tmp_path), 3, bm25,
+                                                  splits, n_repeats=2, repeat_seed=5, batch_size=c["batch_size"])
+    assert mrr["MRR@1"] > 0.8 and mrr["MRR@5"] > 0.99  # bf16 table: a near-tie at rank 1 may swap
+    assert len(orig) == len(splits[1]) and len(perm) == 2 * len(orig)
+    wd = tmp_path / "data_iteration_3"
+    assert torch.load(wd / "ranking_profile.pt") == prof
+    header, rows, permuted, track = O.al0_requests_ref(prof, bm25, c["corpus"], c["queries"], splits, 3, 2, 2, 5)
+    buf = io.StringIO()
+    pd.DataFrame(permuted, columns=header).to_csv(buf, index=False)
+    assert open(wd / "request_perm.csv", "rb").read() == buf.getvalue().encode()
+    assert torch.load(wd / "id_track.pt") == track
+    calls = table.calls
+    ccr.al_rank.rank_step(c["corpus"], c["queries"], qrels, table, str(tmp_path), 3, bm25, splits, 2, 5)
+    assert table.calls == calls  # cached profile: the encoder is not called again
