@@ -140,11 +140,6 @@ __device__ __forceinline__ void tc_mma_bf16_2cta(u32 tmem_d, u64 adesc, u64 bdes
 __device__ __forceinline__ void mbar_arrive_remote(u32 cluster_bar_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
-// relaxed variant (same reasoning as mbar_arrive_relaxed): the hand-back of an accumulator must not
-// wait for the thread's outstanding candidate stores
-__device__ __forceinline__ void mbar_arrive_remote_relaxed(u32 cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(u64* bar) {
@@ -662,10 +657,8 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (kCta == 2) {
-            if (p.debug & 512) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));  // A/B: release arrive
-            else mbar_arrive_remote_relaxed(mapa_u32(&sh->tmem_empty[acc], 0));
-          } else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
+          if (kCta == 2) mbar_arrive_remote(mapa_u32(&sh->tmem_empty[acc], 0));
+          else mbar_arrive_relaxed(&sh->tmem_empty[acc]);
         }
         // two filter call sites (instruction-cache footprint vs register moves): chunks 0,1 are
         // filtered from v,w1; then chunks 2,3 move into those registers and take the same code
