@@ -59,8 +59,6 @@ struct Plan {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr long long kTwoCtaMaxB = 1536;  // largest batch served by CTA pairs (see make_plan)
-
 int splits_tc(int nq, long long tiles, int sms) {
   long long smax = tiles < 1 ? 1 : tiles;
   long long s0 = (sms + nq - 1) / nq;
@@ -90,13 +88,17 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
                       !getenv("CCR_MASK_EXCLUDE")) ? 1 : 0;
   pl->k_keep = pl->include_mask ? (int)(k + h_max) : k;
   if (algo == CCR_ALGO_TCGEN05) {
-    // CTA pairs (cta_group::2, 256 query rows per unit) stream each item tile once for 256 queries
-    // and their GEMM pipeline alone is ~9 % faster.  Measured on B200 (8.84M x 768, k=100, same box,
-    // profiles/r01_midbatch_ab.txt): pairs win for 128 < B <= 1024 (B=256: 2.95 vs 3.27 ms, 512: 5.45
-    // vs 5.87, 1024: 11.3 vs 11.6), tie at 2048, and lose from 3072 up (4096: 47.9 vs 45.0 ms; the
-    // leader's MMA waits for 16 selection warps instead of 8).  A pair pads the batch to 256 rows, so
-    // an odd number of 128-row tiles stays on single CTAs (B=384: 4.72 vs 5.48 ms).
-    pl->two_cta = (B > kQTile && B <= kTwoCtaMaxB && ((B + kQTile - 1) / kQTile) % 2 == 0) ? 1 : 0;
+    // CTA pairs (cta_group::2, 256 query rows per unit) stream each item tile once for 256 queries:
+    // a third less operand traffic from L2 into the SMs and a GEMM pipeline that is ~9 % faster on its
+    // own.  With the bounded-drift throttle (see ccr_score_topk_bf16) they win at every batch size
+    // measured on B200 (8.84M x 768, k=100, same box, profiles/r01_pairs_throttle_ab.txt): B=256 2.95 vs
+    // 3.27 ms, 512 5.7 vs 6.05, 1024 11.2-11.7 vs 12.2, 2048 21.7 vs 23.4, 4096 43.3 vs 46.8, 8192 90.0 vs
+    // 92.6; bench.py's sustained loop 94.3-95.0 k vs 87.1-87.4 k queries/s.  A pair pads the batch to 256
+    // rows, so a small odd number of 128-row tiles stays on single CTAs (B=384: 4.72 vs 5.48 ms).
+    {
+      const long long tiles128 = (B + kQTile - 1) / kQTile;
+      pl->two_cta = (B > kQTile && (tiles128 % 2 == 0 || tiles128 >= 17)) ? 1 : 0;
+    }
     if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
     const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
     pl->n_q_tiles = (int)((B + unit_rows - 1) / unit_rows);
@@ -285,7 +287,14 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.dense_out = nullptr; sp.ld_out = 0;
   sp.progress = nullptr;
   sp.g_hist = nullptr; sp.g_hpar = nullptr;
-  if (pl.algo == CCR_ALGO_TCGEN05 && getenv("CCR_THROTTLE")) {  // opt-in: see DESIGN.md §8
+  // bounded drift between the units that stream the same item split: default for CTA pairs (their
+  // deeper pipeline lets a leader run away from its followers: 99 GB instead of 15 GB of DRAM reads
+  // at B=4096), opt-in for single CTAs where it was measured to cost more than it saves
+  bool use_throttle = pl.two_cta && pl.n_q_tiles > 1;
+  if (const char* t = getenv("CCR_THROTTLE")) use_throttle = atoi(t) != 0;
+  sp.lead_tiles = 16;
+  if (const char* t = getenv("CCR_LEAD")) { int v = atoi(t); if (v >= 1 && v <= 4096) sp.lead_tiles = v; }
+  if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) {
     sp.progress = (int*)(ws + pl.off_progress);
     e = cudaMemsetAsync(sp.progress, 0, (size_t)pl.n_q_tiles * pl.S * sizeof(int), st);
     if (e != cudaSuccess) return fail(CCR_ECUDA, "memset progress: %s", cudaGetErrorString(e));

@@ -49,6 +49,7 @@ struct SelectParams {
   // bounded drift between the CTAs that stream the same item split (keeps their shared item
   // tiles L2-resident so the table is read from HBM once): tiles issued so far, per unit
   int* progress;  // [n_units], zeroed per call; null = off
+  int lead_tiles; // max lead (item tiles) of a producer over the slowest unit on the same split
   // store mode (threshold seeding pre-pass): write fp32 scores instead of selecting
   float* dense_out;      // [rows_pad][ld_out], null in select mode
   long long ld_out;

@@ -40,7 +40,7 @@ constexpr int kTcThreads = 384;                 // 3 warpgroups: warps 0..7 sele
                                                 // move registers from the feeders to the selection warps)
 constexpr int kSelRegs = 216, kFeedRegs = 56;
 constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
-constexpr int kLeadTiles = 16;                  // max lead (item tiles) over the slowest CTA on the same split
+constexpr unsigned long long kThrottleGiveUpNs = 2ull * 1000ull * 1000ull;  // 2 ms
 constexpr int kStageKeys = 384;                 // candidate buffers up to this size are pruned in smem
 constexpr int kTmemCols = 512;
 constexpr unsigned long long kWaitLimitNs = 10ull * 1000ull * 1000ull * 1000ull;  // 10 s
@@ -475,7 +475,14 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           peer_lo = peer_lo > it_lo ? peer_lo : it_lo;
           peer_hi = peer_hi < it_hi ? peer_hi : it_hi;
         }
-        const bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
+        // Units that stream the same split only share its tiles through L2 while they stay close
+        // together.  A leader that is not slowed down by its own L2 misses (the 6-stage pair
+        // pipeline hides them) runs away and every follower then misses too: DRAM reads of 7x the
+        // table were measured for CTA pairs at B=4096.  So a producer never leads the slowest peer by
+        // more than lead_tiles.  Peers run concurrently because the grid has at most one CTA per SM;
+        // should one not be running (shared GPU), the wait gives up after 2 ms and throttling is
+        // dropped for the rest of the unit.
+        bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
         for (long long t = t0; t < t1; ++t) {
           if (throttle && ((t - t0) & 7) == 0) {
             const int mine = (int)(t - t0);
@@ -488,12 +495,12 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(p.progress + v) : "memory");
                 mn = pv < mn ? pv : mn;
               }
-              if (mine - mn <= kLeadTiles) break;
+              if (mine - mn <= p.lead_tiles) break;
               __nanosleep(500);
               unsigned long long now;
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
               if (w0 == 0) w0 = now;
-              else if (now - w0 > kWaitLimitNs) break;  // never deadlock on a peer: give up throttling
+              else if (now - w0 > kThrottleGiveUpNs) { throttle = false; break; }  // never depend on a peer
             }
           }
           for (int kb = 0; kb < num_kb; ++kb) {

@@ -41,7 +41,8 @@ def test_planning_entry_points_work_without_gpu():
     assert L.ccr_choose_algo(4, 8841823, 768, 100) == _lib.ALGO_TCGEN05
     assert L.ccr_choose_algo(512, 1000, 768, 10) == _lib.ALGO_TCGEN05
     info = _lib.plan_info(4096, 8841823, 768, 100)
-    assert info["n_q_tiles"] == 32 and info["cand_capacity"] == 384 and info["n_splits"] >= 5
+    assert info["n_q_tiles"] == 16 and info["cand_capacity"] == 384 and info["n_splits"] >= 5  # 16 CTA-pair tiles
+    assert _lib.plan_info(384, 8841823, 768, 100)["n_q_tiles"] == 3  # odd tile count: single CTAs
 
 
 def test_product_refuses_cpu_tensors():
