@@ -316,9 +316,9 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tflops"],
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
-                     # exact workload (profiles/r01_select_tc_b4096_hist_ncu_raw.csv: 15.22 GB read + 0.10 GB
+                     # exact workload (profiles/r01_select_tc_b4096_pairs_ncu_raw.csv: 16.98 GB read + 0.11 GB
                      # written); algorithmic bytes = 13.58e9
-                     "traffic": 15.32e9 if (world == 1 and B == 4096 and N == N_ITEMS and k == TOPK) else None,
+                     "traffic": 17.09e9 if (world == 1 and B == 4096 and N == N_ITEMS and k == TOPK) else None,
                      "kernel": "select_tc_kernel (tcgen05 GEMM fused with mask + top-k)",
                      "kernel_ms": kern_ms, "peak_source": pk["source"] + ", sustained cuBLAS bf16",
                      "frac_of_burst_peak": achieved / pk["tflops_burst"],

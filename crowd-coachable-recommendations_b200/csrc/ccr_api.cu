@@ -94,10 +94,11 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     // measured on B200 (8.84M x 768, k=100, same box, profiles/r01_pairs_throttle_ab.txt): B=256 2.95 vs
     // 3.27 ms, 512 5.7 vs 6.05, 1024 11.2-11.7 vs 12.2, 2048 21.7 vs 23.4, 4096 43.3 vs 46.8, 8192 90.0 vs
     // 92.6; bench.py's sustained loop 94.3-95.0 k vs 87.1-87.4 k queries/s.  A pair pads the batch to 256
-    // rows, so a small odd number of 128-row tiles stays on single CTAs (B=384: 4.72 vs 5.48 ms).
+    // rows, so a small odd number of 128-row tiles stays on single CTAs (B=384: 4.72 vs 5.48 ms); the
+    // margin shrinks with the number of query tiles per split (8192: 3 %), beyond that single CTAs.
     {
       const long long tiles128 = (B + kQTile - 1) / kQTile;
-      pl->two_cta = (B > kQTile && (tiles128 % 2 == 0 || tiles128 >= 17)) ? 1 : 0;
+      pl->two_cta = (B > kQTile && B <= 8192 && (tiles128 % 2 == 0 || tiles128 >= 17)) ? 1 : 0;
     }
     if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
     const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
