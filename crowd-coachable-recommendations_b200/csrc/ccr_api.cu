@@ -172,6 +172,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     if (m > n_items / 8) m = n_items / 8;
     long long cap = (512LL << 20) / (4LL * pl->rows_pad);
     if (m > cap) m = cap;
+    if (const char* sm = getenv("CCR_SEED_M")) { long long v = atoll(sm); if (v >= 1024 && v < m) m = v; }  // experiment knob
     m = m / 256 * 256;
     if (m >= 1024 && 4LL * pl->k_keep <= m) {
       pl->seed_m = (int)m;
