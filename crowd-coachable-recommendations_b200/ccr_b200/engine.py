@@ -110,6 +110,24 @@ class SparseMask:
         vals = np.full(cols.shape, float(value))
         return cls(indptr, cols, vals, n_cols, mode, device)
 
+    @classmethod
+    def from_flat(cls, row_lengths, cols, n_cols, value, mode, device):
+        """Rows given back to back: ``cols`` holds row 0's columns, then row 1's, ... (duplicates
+        allowed); ``row_lengths[r]`` entries belong to row r.  One vectorised sort instead of a
+        Python loop over rows (block lists of whole brands: ~1.3 M entries for 9,862 queries)."""
+        row_lengths = np.asarray(row_lengths, dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        if cols.size and (cols.min() < 0 or cols.max() >= n_cols):
+            raise IndexError("mask column out of range")
+        row_of = np.repeat(np.arange(len(row_lengths), dtype=np.int64), row_lengths)
+        key = np.sort(row_of * np.int64(n_cols) + cols)     # by (row, col); sort + diff: np.unique is 50x slower
+        if key.size:
+            key = key[np.concatenate(([True], key[1:] != key[:-1]))]
+        rows_u, cols_u = key // n_cols, key % n_cols
+        indptr = np.zeros(len(row_lengths) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows_u, minlength=len(row_lengths)), out=indptr[1:])
+        return cls(indptr, cols_u, np.full(cols_u.shape, float(value)), n_cols, mode, device)
+
     def rows(self, start, stop):
         ip, c, v = self.host
         a, b = ip[start], ip[stop]

@@ -74,17 +74,18 @@ def generate_embeddings_device(data_indices, data_dic, embedding_func, batch_siz
 
 def build_block_mask(queries_ids, corpus_ids, block_dict, device):
     """block_dict {qid: [pid, ...]} -> SparseMask(set -1e6).  Mirrors ms_marco_eval.py:225-227
-    including the "block id not found" assertion, with the pid->position index built once
-    instead of once per query."""
+    including the "block id not found" assertion, with the pid->position index built once and ONE
+    lookup over all block lists instead of one index build + lookup per query."""
     import pandas as pd
 
+    from itertools import chain
+
     index = pd.Index(corpus_ids)
-    rows = []
-    for qid in queries_ids:
-        ind = index.get_indexer(block_dict[qid])
-        assert -1 not in ind, "block id not found"
-        rows.append(ind)
-    return engine.SparseMask.from_lists(rows, len(corpus_ids), BLOCK_VALUE, engine.MASK_SET, device)
+    blocks = [block_dict[qid] for qid in queries_ids]  # KeyError for a query without an entry, like :225
+    lengths = [len(b) for b in blocks]
+    ind = index.get_indexer(list(chain.from_iterable(blocks))) if sum(lengths) else np.zeros(0, dtype=np.int64)
+    assert -1 not in ind, "block id not found"
+    return engine.SparseMask.from_flat(lengths, ind, len(corpus_ids), BLOCK_VALUE, engine.MASK_SET, device)
 
 
 def ranking_tensors(query_table, passage_table, k, mask=None, algo=0):

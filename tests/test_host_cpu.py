@@ -148,3 +148,20 @@ def test_mask_helpers_on_cpu_arrays():
         assert e.nnz == 0 and e.host[0].tolist() == [0, 0, 0, 0]
     finally:
         engine.SparseMask = engine_SparseMask
+
+
+def test_sparse_mask_from_flat_equals_from_lists(monkeypatch):
+    """Vectorised block-mask construction (rows back to back, duplicates, empty rows) builds the
+    same CSR as the per-row path; device upload stubbed out (host logic only)."""
+    from ccr_b200 import engine
+
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a, **k: self)
+    rs = np.random.RandomState(0)
+    rows = [rs.randint(0, 50, size=rs.randint(0, 12)) for _ in range(40)] + [np.zeros(0, dtype=np.int64)]
+    a = engine.SparseMask.from_lists(rows, 50, -1e6, engine.MASK_SET, "cpu")
+    b = engine.SparseMask.from_flat([len(r) for r in rows], np.concatenate(rows), 50, -1e6, engine.MASK_SET, "cpu")
+    for x, y in zip(a.host, b.host):
+        np.testing.assert_array_equal(x, y)
+    assert a.max_row_nnz == b.max_row_nnz and b.n_rows == 41
+    with pytest.raises(IndexError):
+        engine.SparseMask.from_flat([1], [50], 50, -1e6, engine.MASK_SET, "cpu")
