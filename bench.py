@@ -84,7 +84,7 @@ def cpu_reference_step(sample_items, sample_queries, seed=0):
     return time.perf_counter() - t0
 
 
-def cpu_baseline(n_items, sample_items=1 << 20, sample_queries=24):
+def cpu_baseline(n_items, sample_items=1 << 20, sample_queries=96):
     dt = cpu_reference_step(sample_items, sample_queries)
     qps_sample = sample_queries / dt
     return {
@@ -104,7 +104,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_items, sample_queries = 1 << 20, 24
+    sample_items, sample_queries = 1 << 20, 96
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_reference_step(sample_items, 4)
     times = [cpu_reference_step(sample_items, sample_queries, seed=i) for i in range(max(1, min(args.steps, 3)))]

@@ -21,6 +21,7 @@ from .score_array import (  # noqa: F401
     LazySparseMatrix,
     MatMulExpression,
     auto_cast_lazy_score,
+    dense_plan,
     fused_plan,
     get_batch_size,
     score_op,

@@ -343,3 +343,47 @@ def fused_plan(S):
     if tuple(mm.shape) != shape or any(tuple(c.shape) != shape for _, c in sparse_terms):
         return None  # broadcasting terms are left to the generic path
     return FusedPlan(mm.left, mm.right, sparse_terms, shape)
+
+
+class DensePlan:
+    """An already materialised dense score matrix plus the summed sparse additive term (or None):
+    what the reference's unmodified ``BertBPR.transform(D) + D.prior_score`` evaluates to
+    (src/ccrec/models/bbpr.py:550, src/ccrec/models/bert_mt.py:376)."""
+
+    def __init__(self, dense, sparse_terms, shape):
+        self.dense, self.shape = dense, shape
+        self.sparse = None
+        for sign, csr in sparse_terms:
+            term = csr if sign > 0 else -csr
+            self.sparse = term if self.sparse is None else self.sparse + term
+        if self.sparse is not None:
+            self.sparse = sps.csr_matrix(self.sparse, dtype=np.float64)
+
+
+def dense_plan(S):
+    """Return a DensePlan when ``S`` is one LazyDenseMatrix optionally plus / minus LazySparse
+    terms, all of the full shape; ``None`` for every other expression."""
+    leaves, sparse_terms = [], []
+
+    def walk(node, sign):
+        if isinstance(node, LazyDenseMatrix):
+            if sign < 0:
+                return False
+            leaves.append(node)
+            return True
+        if isinstance(node, LazySparseMatrix):
+            sparse_terms.append((sign, node.c))
+            return True
+        if isinstance(node, ElementWiseExpression) and len(node.children) == 2:
+            if node.op is operator.add:
+                return walk(node.children[0], sign) and walk(node.children[1], sign)
+            if node.op is operator.sub:
+                return walk(node.children[0], sign) and walk(node.children[1], -sign)
+        return False
+
+    if not walk(S, +1) or len(leaves) != 1:
+        return None
+    shape = tuple(S.shape)
+    if tuple(leaves[0].shape) != shape or any(tuple(c.shape) != shape for _, c in sparse_terms):
+        return None
+    return DensePlan(leaves[0], sparse_terms, shape)

@@ -18,7 +18,7 @@ import scipy.sparse as sps
 import torch
 
 from . import engine
-from .score_array import LazyScoreBase, auto_cast_lazy_score, fused_plan
+from .score_array import LazyScoreBase, auto_cast_lazy_score, dense_plan, fused_plan
 from .table import EmbeddingTable
 
 ROW_CHUNK = 8192
@@ -34,11 +34,47 @@ def _device_table_for(right):
     return t
 
 
+DENSE_CHUNK_ELEMS = 1 << 27  # dense score elements ranked per device pass (1 GB of float64)
+
+
+def _topk_materialised(plan, k, want_scores):
+    """Top-k of an already materialised dense score matrix (+ sparse prior): the reference's
+    ``as_tensor`` semantics exactly -- the dense leaf keeps its dtype, adding the float64 CSR
+    promotes to float64 (src/rime_lite/util/score_array.py:173-174,291-293) -- ranked on the
+    device by a stable descending sort (ties -> lowest column; a library sort: this shape only
+    occurs on small reranking sets and is not the hot path, like ``_argsort``)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("ccr_b200 needs a CUDA device (no CPU path)")
+    dev = torch.device("cuda")
+    B, N = plan.shape
+    if k > N:
+        raise RuntimeError("selected index k out of range")
+    ids = np.empty((B, k), dtype=np.int64)
+    vals = np.empty((B, k), dtype=np.float64) if want_scores else None
+    rows_per = max(1, DENSE_CHUNK_ELEMS // max(1, N))
+    for s in range(0, B, rows_per):
+        e = min(B, s + rows_per)
+        dense = torch.as_tensor(np.ascontiguousarray(plan.dense.c[s:e])).to(dev)
+        if plan.sparse is not None:
+            coo = plan.sparse[s:e].tocoo()
+            dense = dense.double()
+            dense.index_put_((torch.as_tensor(coo.row, dtype=torch.int64, device=dev),
+                              torch.as_tensor(coo.col, dtype=torch.int64, device=dev)),
+                             torch.as_tensor(coo.data, dtype=torch.float64, device=dev), accumulate=True)
+        top, order = torch.sort(dense, dim=1, descending=True, stable=True)
+        ids[s:e] = order[:, :k].cpu().numpy()
+        if want_scores:
+            vals[s:e] = top[:, :k].double().cpu().numpy()
+    return (ids, vals) if want_scores else ids
+
+
 def topk_lazy(S, k, want_scores=False, algo=0):
-    """(ids [B,k] int64 numpy[, scores64 [B,k]]) for a fused-plan expression; None if S is not one."""
+    """(ids [B,k] int64 numpy[, scores64 [B,k]]) for a fused-plan expression (factor pair: the
+    fused kernel) or a materialised dense matrix (+ priors); None if S is neither."""
     plan = fused_plan(S)
     if plan is None:
-        return None
+        dplan = dense_plan(S)
+        return _topk_materialised(dplan, k, want_scores) if dplan is not None else None
     B, N = plan.shape
     if k > N:
         raise RuntimeError("selected index k out of range")
@@ -67,7 +103,8 @@ def _assign_topk(S, k, tie_breaker=1e-10, device="cpu", batch_size=None):
     if indices is None:
         raise NotImplementedError(
             f"_assign_topk: expression {S!r} is outside the accelerated score-and-rank path "
-            "(supported: LazyDense @ LazyDense.T [+/- sparse priors]); see DESIGN.md 'out of scope'")
+            "(supported: LazyDense @ LazyDense.T [+/- sparse priors], LazyDense [+/- sparse priors]); "
+            "see DESIGN.md 'out of scope'")
     return sps.csr_matrix(
         (np.ones(indices.size), np.ravel(indices), np.arange(0, indices.size + 1, indices.shape[1])),
         shape=S.shape,

@@ -346,3 +346,24 @@ def test_al0_rank_step_end_to_end(ccr, tmp_path, monkeypatch):
     calls = table.calls
     ccr.al_rank.rank_step(c["corpus"], c["queries"], qrels, table, str(tmp_path), 3, bm25, splits, 2, 5)
     assert table.calls == calls  # cached profile: the encoder is not called again
+
+
+@pytest.mark.parametrize("name", list(cases.RIME_CASES))
+def test_assign_topk_on_materialised_matrix_is_bit_exact(ccr, name, golden_dir):
+    """The reference's unmodified ``transform`` hands ``_assign_topk`` a dense host matrix (+ prior):
+    same fp32 matrix in -> the reference's own indices out, exactly (no bf16 anywhere)."""
+    g = np.load(os.path.join(golden_dir, f"rime_{name}.npz"))
+    c = cases.rime_case(name)
+    dense = O.lazy_score_dense_ref(c["U"], c["V"], None).numpy()  # fp32 U @ V.T as the reference builds it
+    S = ccr.LazyDenseMatrix(dense)
+    if c["prior"] is not None:
+        S = S + c["prior"]
+    csr = ccr._assign_topk(S, c["k"])
+    np.testing.assert_array_equal(csr.indices.reshape(len(c["U"]), c["k"]), g["indices"])
+    np.testing.assert_array_equal(csr.indptr, g["indptr"])
+    m = ccr.evaluate_item_rec((csr > 0).astype(np.float64), S, c["k"])
+    want = dict(zip(g["metric_names"].tolist(), g["metric_values"].tolist()))
+    for key, v in want.items():
+        assert abs(m[key] - v) <= 1e-9 * max(1.0, abs(v)), (key, m[key], v)
+    csr2 = ccr._assign_topk(dense if c["prior"] is None else S, c["k"])  # plain ndarray input too
+    np.testing.assert_array_equal(csr2.indices, csr.indices)
