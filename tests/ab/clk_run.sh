@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: tests/clk_run.sh <label> <env...> -- args to ncu_case.py ; samples SM clock / power while running
+# usage: tests/ab/clk_run.sh <label> <env...> -- args to ncu_case.py ; samples SM clock / power while running
 label=$1; shift
 nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_event_reasons.active --format=csv,noheader -lms 100 > /tmp/clk_$label.csv &
 SMI=$!

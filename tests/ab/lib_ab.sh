@@ -1,5 +1,5 @@
 #!/bin/bash
-# alternate two builds of the library on the same box: tests/lib_ab.sh B N k rounds
+# alternate two builds of the library on the same box: tests/ab/lib_ab.sh B N k rounds
 B=$1; N=$2; K=$3; R=${4:-3}
 PREV=crowd-coachable-recommendations_b200/lib/libccr_b200_prev.so
 for i in $(seq $R); do
