@@ -276,12 +276,17 @@ SEEDED_CASES = [
     (256, 270_000, 64, 100, O.MASK_ADD, "dot", "1"),
     (130, 400_000, 64, 2048, O.MASK_NONE, "cos", "0"),
     (5, 300_000, 128, 100, O.MASK_SET, "dot", "0"),
+    # default policy (None): several query tiles per item split -> CTA pairs + bounded-drift throttle
+    (2304, 280_000, 64, 50, O.MASK_NONE, "dot", None),
+    (1100, 300_000, 64, 100, O.MASK_SET, "dot", None),   # 9 tiles: odd -> single CTAs, two waves
+    (4200, 270_000, 64, 10, O.MASK_ADD, "dot", None),    # 33 tiles -> 17 pair tiles, padded rows
 ]
 
 
 @pytest.mark.parametrize("B,N,D,k,mode,sim,two", SEEDED_CASES)
 def test_seeded_histogram_path_matches_oracle(ccr, B, N, D, k, mode, sim, two, monkeypatch):
-    monkeypatch.setenv("CCR_2CTA", two)
+    if two is not None:
+        monkeypatch.setenv("CCR_2CTA", two)
     dev = torch.device("cuda:0")
     rs = np.random.RandomState(B + k)
     P = cases.embeddings(B * 7 + k, N, D, clustered=(sim == "cos"))
