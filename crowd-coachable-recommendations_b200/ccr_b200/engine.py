@@ -60,9 +60,16 @@ class SparseMask:
                      np.asarray(vals, dtype=np.float64))
         self.max_row_nnz = int(np.diff(self.host[0]).max()) if self.n_rows else 0
         self.device = torch.device(device)
-        self.indptr = torch.as_tensor(self.host[0]).to(self.device)
-        self.cols = torch.as_tensor(self.host[1]).to(self.device)
-        self.vals = torch.as_tensor(self.host[2]).to(self.device)
+        # pinned staging + non-blocking copies: a pageable upload would make the host wait for all
+        # queued device work (per-step mask shards of a row-sharded search are built on the host)
+        self.indptr, self.cols, self.vals = (self._upload(a) for a in self.host)
+
+    def _upload(self, a):
+        t = torch.as_tensor(a)
+        if self.device.type == "cuda" and t.numel():
+            return t.pin_memory().to(self.device, non_blocking=True)
+        return t.to(self.device)
+
 
     @classmethod
     def from_device_tensors(cls, indptr, cols, vals, host, n_cols, mode):

@@ -40,6 +40,8 @@ class bench:  # the constants / generators of bench.py, restated so this script 
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if len(sys.argv) > 3:
+    bench.N_ITEMS = int(sys.argv[3])  # e.g. 1105228 = one rank's shard at 8 GPUs
 dev = torch.device("cuda:0")
 table = ccr_b200.EmbeddingTable(bench.N_ITEMS, bench.DIM, device=dev)
 bench.build_shard(table, 0, bench.N_ITEMS, dev)
