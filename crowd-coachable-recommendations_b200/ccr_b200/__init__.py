@@ -12,7 +12,7 @@ Public surface (mirrors the reference's call sites for this path):
 * ``score_topk`` / ``merge_topk``                          (thin wrappers of the C ABI)
 """
 from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, MASK_ADD, MASK_NONE, MASK_SET, LIB_PATH  # noqa: F401
-from .engine import SparseMask, ingest_rows, merge_topk, score_dense, score_topk  # noqa: F401
+from .engine import SparseMask, ingest_rows, merge_topk, score_dense, score_topk, topk_dense  # noqa: F401
 from .table import EmbeddingTable  # noqa: F401
 from .score_array import (  # noqa: F401
     ElementWiseExpression,

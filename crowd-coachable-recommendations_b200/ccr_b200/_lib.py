@@ -13,7 +13,7 @@ MASK_NONE, MASK_SET, MASK_ADD = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 FLAG_ALLOW_SHORT = 0x10
 MAX_K = 2048
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, EK_RANGE = 0, -1, -2, -3, -4, -5
 
@@ -30,6 +30,8 @@ EXPORTS = [
     "ccr_choose_algo",
     "ccr_plan_info",
     "ccr_set_profile_events",
+    "ccr_topk_dense_workspace_bytes",
+    "ccr_topk_dense_f32",
     "ccr_bm25_build_impacts",
     "ccr_bm25_topk_workspace_bytes",
     "ccr_bm25_topk",
@@ -81,6 +83,10 @@ def lib():
     L.ccr_plan_info.restype = i32
     L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i32, c.POINTER(c.c_int32)]
     f64 = c.c_double
+    L.ccr_topk_dense_workspace_bytes.restype = sz
+    L.ccr_topk_dense_workspace_bytes.argtypes = [i64, i64, i32, i64, i64]
+    L.ccr_topk_dense_f32.restype = i32
+    L.ccr_topk_dense_f32.argtypes = [vp, i64, i64, i64, i32, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, sz, vp]
     L.ccr_bm25_build_impacts.restype = i32
     L.ccr_bm25_build_impacts.argtypes = [vp, vp, vp, vp, vp, f64, i64, i64, vp, vp]
     L.ccr_bm25_topk_workspace_bytes.restype = sz

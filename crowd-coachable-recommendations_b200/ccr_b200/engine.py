@@ -218,6 +218,36 @@ def merge_topk(scores64, ids, k_out):
     return out_s, out_i, out_d
 
 
+def topk_dense(scores, k, mask: SparseMask | None = None):
+    """Top-k of a materialised float32 score matrix [B, N] on the device (+ sparse prior, float64
+    like the reference's promotion): C ABI ccr_topk_dense_f32.  Returns (scores f32, ids i64, scores f64)."""
+    _require_cuda(scores, "scores")
+    if scores.dtype != torch.float32 or scores.dim() != 2 or (scores.shape[1] and scores.stride(1) != 1):
+        raise TypeError("scores must be a 2-d float32 tensor with a contiguous last dimension")
+    B, N = scores.shape
+    k = int(k)
+    dev = scores.device
+    ld = scores.stride(0) if B > 1 else max(scores.stride(0), N)
+    if mask is not None and (mask.n_rows != B or mask.n_cols != N):
+        raise ValueError("mask shape does not match the score matrix")
+    nnz = mask.nnz if mask is not None else 0
+    hmax = mask.max_row_nnz if mask is not None else 0
+    out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
+    out_d = torch.empty((B, k), dtype=torch.float64, device=dev)
+    out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.ccr_topk_dense_workspace_bytes(B, N, k, nnz, hmax)
+        ws = workspace.get(dev, max(need, 256))
+        rc = L.ccr_topk_dense_f32(
+            scores.data_ptr(), B, N, ld, k,
+            mask.indptr.data_ptr() if nnz else None, mask.cols.data_ptr() if nnz else None,
+            mask.vals.data_ptr() if nnz else None, nnz, hmax, mask.mode if nnz else MASK_NONE,
+            out_s.data_ptr(), out_d.data_ptr(), out_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc)
+    return out_s, out_i, out_d
+
+
 def ingest_rows(src, dst, normalize=False):
     """fp32 (or bf16) rows on the device -> bf16 table rows, optional fp32 L2 normalisation."""
     _require_cuda(src, "src")

@@ -17,7 +17,7 @@ import numpy as np
 import scipy.sparse as sps
 import torch
 
-from . import engine
+from . import _lib, engine
 from .score_array import LazyScoreBase, auto_cast_lazy_score, dense_plan, fused_plan
 from .table import EmbeddingTable
 
@@ -38,11 +38,13 @@ DENSE_CHUNK_ELEMS = 1 << 27  # dense score elements ranked per device pass (1 GB
 
 
 def _topk_materialised(plan, k, want_scores):
-    """Top-k of an already materialised dense score matrix (+ sparse prior): the reference's
-    ``as_tensor`` semantics exactly -- the dense leaf keeps its dtype, adding the float64 CSR
-    promotes to float64 (src/rime_lite/util/score_array.py:173-174,291-293) -- ranked on the
-    device by a stable descending sort (ties -> lowest column; a library sort: this shape only
-    occurs on small reranking sets and is not the hot path, like ``_argsort``)."""
+    """Top-k of an already materialised dense score matrix (+ sparse prior) with the reference's
+    ``as_tensor`` semantics -- the dense leaf keeps its dtype, adding the float64 CSR promotes to
+    float64 (src/rime_lite/util/score_array.py:173-174,291-293).  float32 (and narrower) leaves,
+    i.e. everything the reference's ``transform`` produces, run through the C ABI
+    (``ccr_topk_dense_f32``: streaming exact top-k, priors merged as float64 overrides).  A float64
+    leaf would need 64-bit score keys; that corner (never produced by the reference's own callers)
+    is ranked by a stable device sort instead.  Ties -> lowest column either way."""
     if not torch.cuda.is_available():
         raise RuntimeError("ccr_b200 needs a CUDA device (no CPU path)")
     dev = torch.device("cuda")
@@ -51,10 +53,23 @@ def _topk_materialised(plan, k, want_scores):
         raise RuntimeError("selected index k out of range")
     ids = np.empty((B, k), dtype=np.int64)
     vals = np.empty((B, k), dtype=np.float64) if want_scores else None
-    rows_per = max(1, DENSE_CHUNK_ELEMS // max(1, N))
+    leaf = np.asarray(plan.dense.c)
+    native = leaf.dtype in (np.float32, np.float16) and k <= _lib.MAX_K
+    mask_all = None
+    if native and plan.sparse is not None:
+        mask_all = engine.SparseMask.from_scipy(plan.sparse, engine.MASK_ADD, dev)
+        native = k + mask_all.max_row_nnz <= _lib.MAX_K
+    rows_per = max(1, min(DENSE_CHUNK_ELEMS // max(1, N), 65535))
     for s in range(0, B, rows_per):
         e = min(B, s + rows_per)
-        dense = torch.as_tensor(np.ascontiguousarray(plan.dense.c[s:e])).to(dev)
+        dense = torch.as_tensor(np.ascontiguousarray(leaf[s:e])).to(dev)
+        if native:
+            m = mask_all.rows(s, e) if mask_all is not None else None
+            _, order, top = engine.topk_dense(dense.float(), k, mask=m)
+            ids[s:e] = order.cpu().numpy()
+            if want_scores:
+                vals[s:e] = top.cpu().numpy()
+            continue
         if plan.sparse is not None:
             coo = plan.sparse[s:e].tocoo()
             dense = dense.double()

@@ -424,6 +424,78 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
   return CCR_OK;
 }
 
+// ---- top-k of a materialised dense score matrix ----
+struct DensePlanC { int S, C; size_t off_counts, off_ovr_hi, off_ovr_lo, total; };
+static void dense_plan(long long B, long long N, int k_keep, long long nnz, DensePlanC* pl) {
+  const int sms = device_sm_count();
+  const long long rows = B > 0 ? B : 1;
+  long long s = (8LL * sms + rows - 1) / rows;  // 8 blocks of 256 threads per SM
+  const long long chunks = (N + kDenseSlack - 1) / kDenseSlack;
+  if (s > chunks) s = chunks;
+  if (s > 1024) s = 1024;  // finalize: kFinMaxStreams
+  if (s < 1) s = 1;
+  pl->S = (int)s;
+  pl->C = cand_capacity(k_keep, kDenseSlack);
+  size_t off = align_up((size_t)rows * s * pl->C * sizeof(u64), 256);
+  pl->off_counts = off; off = align_up(off + (size_t)rows * s * sizeof(int), 256);
+  pl->off_ovr_hi = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u64), 256);
+  pl->off_ovr_lo = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u32), 256);
+  pl->total = off;
+}
+
+size_t ccr_topk_dense_workspace_bytes(int64_t B, int64_t n_cols, int k, int64_t mask_nnz, int64_t mask_max_row_nnz) {
+  if (B < 0 || n_cols < 0 || k < 1 || k > CCR_MAX_K || mask_nnz < 0) return 0;
+  const long long h = mask_nnz > 0 ? mask_max_row_nnz : 0;
+  if (h < 0 || k + h > CCR_MAX_K) return 0;
+  DensePlanC pl;
+  dense_plan(B, n_cols, (int)(k + h), mask_nnz, &pl);
+  return pl.total;
+}
+
+int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t ld, int k, const int64_t* mask_indptr,
+                       const int32_t* mask_cols, const double* mask_vals, int64_t mask_nnz, int64_t mask_max_row_nnz,
+                       int mask_mode, float* out_scores, double* out_scores64, int64_t* out_ids, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (B < 0 || n_cols < 0 || ld < n_cols) return fail(CCR_EINVAL, "bad dense top-k shape");
+  if (B > 65535) return fail(CCR_EUNSUPPORTED, "dense top-k: more than 65535 rows per call");
+  if (k < 1 || k > CCR_MAX_K) return fail(CCR_EUNSUPPORTED, "k=%d outside [1,%d]", k, CCR_MAX_K);
+  if (k > n_cols) return fail(CCR_EK_RANGE, "selected index k out of range (k=%d > n=%lld)", k, (long long)n_cols);
+  if (n_cols > (1LL << 31) - 512) return fail(CCR_EUNSUPPORTED, "n_cols must be < 2^31");
+  if (mask_mode != CCR_MASK_NONE && mask_mode != CCR_MASK_SET && mask_mode != CCR_MASK_ADD)
+    return fail(CCR_EINVAL, "bad mask_mode %d", mask_mode);
+  if (B == 0) return CCR_OK;
+  if (!scores || !out_ids) return fail(CCR_EINVAL, "null pointer");
+  const bool has_mask = mask_mode != CCR_MASK_NONE && mask_indptr != nullptr && mask_nnz > 0;
+  if (has_mask && (!mask_cols || !mask_vals)) return fail(CCR_EINVAL, "mask_cols / mask_vals null");
+  const long long nnz = has_mask ? mask_nnz : 0;
+  const long long h = has_mask ? mask_max_row_nnz : 0;
+  if (h < 0 || k + h > CCR_MAX_K)
+    return fail(CCR_EUNSUPPORTED, "dense top-k: k + max row nnz = %lld outside [1,%d]", (long long)(k + h), CCR_MAX_K);
+  DensePlanC pl;
+  dense_plan(B, n_cols, (int)(k + h), nnz, &pl);
+  if (!workspace || workspace_bytes < pl.total) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, pl.total);
+  unsigned char* ws = (unsigned char*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* indptr = has_mask ? (const long long*)mask_indptr : nullptr;
+  int lr = launch_select_dense(scores, ld, B, n_cols, k, indptr, pl.C, pl.S, (u64*)ws, (int*)(ws + pl.off_counts), st);
+  if (lr) return fail(CCR_ECUDA, "dense select launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  if (has_mask) {
+    lr = launch_override_dense(scores, ld, (int)B, n_cols, indptr, mask_cols, mask_vals, nnz, mask_mode,
+                               (u64*)(ws + pl.off_ovr_hi), (u32*)(ws + pl.off_ovr_lo), st);
+    if (lr) return fail(CCR_ECUDA, "dense override launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  }
+  FinalizeParams fp;
+  fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + pl.off_counts);
+  fp.g_tau = nullptr;
+  fp.drop_cols = has_mask ? mask_cols : nullptr;
+  fp.mask_indptr = indptr;
+  fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
+  fp.id_offset = 0; fp.out_scores = out_scores; fp.out_scores64 = out_scores64; fp.out_ids = (long long*)out_ids;
+  lr = launch_finalize(fp, st);
+  if (lr) return fail(CCR_ECUDA, "finalize launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
 // ---- BM25 (lexical sibling of the dense path) ----
 static void bm25_plan(long long Bq, long long N, int k, int* S, int* C, size_t* off_counts, size_t* total) {
   const int sms = device_sm_count();

@@ -765,4 +765,95 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
   return (int)cudaGetLastError();
 }
 
+// =======================================================================================
+// Top-k of an already materialised dense float32 score matrix (+ sparse priors): what the
+// reference's `_assign_topk` receives when `BertBPR.transform` hands it the dense host matrix
+// (src/rime_lite/util/__init__.py:135-141 after score_array.py:226-227 [+ :173-174]).
+//   select_dense_kernel  : block = (column split, row); streams the row, threshold filter,
+//                          candidate buffer, exact radix prune -- the protocol of the fused kernels.
+//                          Rows with priors keep k + nnz(row) candidates (include mode) ...
+//   override_dense_kernel: ... and every prior entry gets its exact float64 value
+//                          double(score) + prior (or the prior itself in SET mode), merged and the
+//                          plain candidates of those columns dropped by finalize_kernel.
+// =======================================================================================
+constexpr int kDenseThreads = 256;
+
+__global__ void __launch_bounds__(kDenseThreads) select_dense_kernel(const float* __restrict__ scores, long long ld,
+                                                                     long long N, int k,
+                                                                     const long long* __restrict__ mask_indptr, int C,
+                                                                     int S, u64* cand, int* counts) {
+  __shared__ int s_cnt;
+  __shared__ float s_tau_f;
+  __shared__ u64 s_tau_key;
+  __shared__ u32 s_hist[256];
+  const int tid = threadIdx.x, split = blockIdx.x;
+  const long long row = blockIdx.y;
+  const int k_row = k + (mask_indptr ? (int)(mask_indptr[row + 1] - mask_indptr[row]) : 0);
+  long long per = (N + S - 1) / S;
+  per = (per + kDenseSlack - 1) / kDenseSlack * kDenseSlack;
+  const long long i0 = (long long)split * per;
+  long long i1 = i0 + per;
+  if (i1 > N) i1 = N;
+  u64* buf = cand + ((long long)row * S + split) * C;
+  const float* r = scores + row * ld;
+  if (tid == 0) { s_cnt = 0; s_tau_f = -INFINITY; s_tau_key = 0ull; }
+  __syncthreads();
+  for (long long base = i0; base < i1; base += kDenseSlack) {
+#pragma unroll
+    for (int j = 0; j < kDenseSlack / kDenseThreads; ++j) {
+      const long long i = base + j * kDenseThreads + tid;
+      if (i < i1) {
+        const float sc = __ldg(r + i);
+        if (sc >= s_tau_f) {  // NaN scores never rank (torch would put them first; the reference has none)
+          const u64 key = make_key(sc, (u32)i);
+          if (key > s_tau_key) buf[atomicAdd(&s_cnt, 1)] = key;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_cnt > C - kDenseSlack) {  // uniform: read after the barrier; C >= 2 * k_row + slack
+      if (tid < 32) {
+        const u64 pivot = warp_prune(buf, s_cnt, k_row, smem_addr(s_hist), 0u);
+        if (tid == 0) { s_cnt = k_row; s_tau_key = pivot; s_tau_f = key_score(pivot); }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counts[(long long)row * S + split] = s_cnt;
+}
+
+__global__ void __launch_bounds__(256) override_dense_kernel(const float* __restrict__ scores, long long ld, int B,
+                                                             long long N, const long long* __restrict__ mask_indptr,
+                                                             const int* __restrict__ mask_cols,
+                                                             const double* __restrict__ mask_vals, long long nnz,
+                                                             int mode, u64* ovr_hi, u32* ovr_lo) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nnz) return;
+  int lo = 0, hi = B;  // row of entry e: largest r with indptr[r] <= e
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (mask_indptr[mid] <= e) lo = mid; else hi = mid; }
+  const int col = mask_cols[e];
+  if (col < 0 || (long long)col >= N) { ovr_hi[e] = 0ull; ovr_lo[e] = 0u; return; }
+  const double val = mode == 1 ? mask_vals[e] : (double)scores[(long long)lo * ld + col] + mask_vals[e];
+  const u64 h = ord64(val);
+  ovr_hi[e] = h ? h : 1ull;
+  ovr_lo[e] = 0xFFFFFFFFu - (u32)col;
+}
+
+int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k,
+                        const long long* mask_indptr, int C, int S, u64* cand, int* counts, cudaStream_t st) {
+  if (B <= 0) return 0;
+  dim3 grid((unsigned)S, (unsigned)B);
+  select_dense_kernel<<<grid, kDenseThreads, 0, st>>>(scores, ld, N, k, mask_indptr, C, S, cand, counts);
+  return (int)cudaGetLastError();
+}
+
+int launch_override_dense(const float* scores, long long ld, int B, long long N, const long long* mask_indptr,
+                          const int* mask_cols, const double* mask_vals, long long nnz, int mode, u64* ovr_hi,
+                          u32* ovr_lo, cudaStream_t st) {
+  if (nnz <= 0) return 0;
+  override_dense_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(scores, ld, B, N, mask_indptr, mask_cols,
+                                                                      mask_vals, nnz, mode, ovr_hi, ovr_lo);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace ccr

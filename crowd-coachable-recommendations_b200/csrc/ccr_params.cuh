@@ -111,6 +111,14 @@ int launch_normalize_bf16(const __nv_bfloat16* src, long long n, int D, long lon
 int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const __nv_bfloat16* items,
                      long long n, long long ldi, int D, float* out, long long ld_out, cudaStream_t st);
 
+// dense top-k (ccr_kernels.cu)
+constexpr int kDenseSlack = 1024;  // columns one block scans between two prune checks
+int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k,
+                        const long long* mask_indptr, int C, int S, u64* cand, int* counts, cudaStream_t st);
+int launch_override_dense(const float* scores, long long ld, int B, long long N, const long long* mask_indptr,
+                          const int* mask_cols, const double* mask_vals, long long nnz, int mode, u64* ovr_hi,
+                          u32* ovr_lo, cudaStream_t st);
+
 // BM25 (ccr_kernels.cu)
 constexpr int kBmChunk = 8192;     // docs per shared-memory accumulator pass (64 KB of float64)
 constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CCR_ABI_VERSION 3
+#define CCR_ABI_VERSION 4
 
 /* error codes */
 #define CCR_OK 0
@@ -132,6 +132,22 @@ int ccr_normalize_rows_bf16(const void* src, int64_t n, int D, int64_t ld_src,
  */
 int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
                         int64_t ldi, int D, float* out, int64_t ld_out, void* stream);
+
+/*
+ * Top-k of an ALREADY MATERIALISED dense float32 score matrix plus an optional sparse prior: the
+ * `_assign_topk` call the reference makes when `BertBPR.transform` hands it the dense users x items
+ * host matrix (src/rime_lite/util/__init__.py:135-141 on the tensor built by
+ * src/rime_lite/util/score_array.py:226-227 [+ :173-174 for the float64 CSR]).
+ *   scores [B, ld] float32 on the device; mask as in ccr_score_topk_bf16 (CSR over columns, float64
+ *   values): CCR_MASK_ADD ranks double(score) + value, CCR_MASK_SET ranks the value itself -- the
+ *   float64 promotion of the reference; columns without an entry rank by their float32 score.
+ *   Output: descending, ties -> lowest column.  B <= 65535, k + mask_max_row_nnz <= CCR_MAX_K.
+ */
+size_t ccr_topk_dense_workspace_bytes(int64_t B, int64_t n_cols, int k, int64_t mask_nnz, int64_t mask_max_row_nnz);
+int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t ld, int k, const int64_t* mask_indptr,
+                       const int32_t* mask_cols, const double* mask_vals, int64_t mask_nnz, int64_t mask_max_row_nnz,
+                       int mask_mode, float* out_scores, double* out_scores64, int64_t* out_ids, void* workspace,
+                       size_t workspace_bytes, void* stream);
 
 /*
  * BM25 -- the lexical sibling of the dense path.  Replaces BM25.transform (scripts/bm_25.py:27-45)
