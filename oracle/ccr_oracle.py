@@ -26,8 +26,10 @@ reference's setup.py:10-17): ``@``/``mm``, ``F.normalize``, ``Tensor.sort``,
 Pinning: the reference ships NO test, golden vector or fixture for this path
 (test/ only holds test_dawid_skene.py).  The oracle is therefore pinned against
 outputs of the reference's own code executed in the build container
-(tests/golden/make_golden.py imports the unmodified reference and stores its
-outputs in tests/golden/*.npz; tests/test_oracle_golden.py replays them).
+(tests/golden/make_golden.py imports the unmodified reference -- or, for the
+non-importable al_0_rank.py, executes its statements read from the file -- and stores
+the outputs in tests/golden/*.npz; tests/test_oracle_golden.py and
+tests/test_al_rank_cpu.py replay them).
 
 ``score_topk_ref`` is the arbiter for the CUDA kernels: fp32 (or fp64 when an
 additive float64 prior is present, as in the reference) scores from the
