@@ -695,10 +695,12 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
         }
         e += kBmThreads;
       }
-      while (more) {  // a doc occurs at most once per term: no conflicts inside an iteration
-        // kBmUnroll x 512 postings per iteration, all loads issued before the first use
-        int doc[kBmUnroll];
-        double v[kBmUnroll];
+      if (more) {
+        // long list: kBmUnroll x 512 postings per iteration, double buffered -- the loads of the
+        // next batch are issued (speculatively: harmless beyond the chunk, guarded by `end`) before
+        // the current batch is applied, so their latency overlaps the accumulate + barrier steps
+        int doc[kBmUnroll], ndoc[kBmUnroll];
+        double v[kBmUnroll], nv[kBmUnroll];
 #pragma unroll
         for (int u = 0; u < kBmUnroll; ++u) {
           const long long i = e + u * kBmThreads + tid;
@@ -706,19 +708,31 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
           doc[u] = live ? __ldg(post_docs + i) : 0x7fffffff;
           v[u] = live ? __ldg(post_val + i) : 0.0;
         }
+        while (more) {  // a doc occurs at most once per term: no conflicts inside an iteration
+          const long long en = e + (long long)kBmUnroll * kBmThreads;
 #pragma unroll
-        for (int u = 0; u < kBmUnroll; ++u) {
-          if (more) {  // uniform
-            const bool in = (long long)doc[u] < c1;
-            if (in) acc[doc[u] - (int)c0] += v[u];
-            const int n_in = __syncthreads_count(in);
-            if (n_in < kBmThreads) {
-              if (tid == n_in) { cur[t] = e + u * kBmThreads + n_in; nxt[t] = doc[u]; }  // first posting beyond
-              more = false;
+          for (int u = 0; u < kBmUnroll; ++u) {
+            const long long i = en + u * kBmThreads + tid;
+            const bool live = i < end;
+            ndoc[u] = live ? __ldg(post_docs + i) : 0x7fffffff;
+            nv[u] = live ? __ldg(post_val + i) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kBmUnroll; ++u) {
+            if (more) {  // uniform
+              const bool in = (long long)doc[u] < c1;
+              if (in) acc[doc[u] - (int)c0] += v[u];
+              const int n_in = __syncthreads_count(in);
+              if (n_in < kBmThreads) {
+                if (tid == n_in) { cur[t] = e + u * kBmThreads + n_in; nxt[t] = doc[u]; }  // first posting beyond
+                more = false;
+              }
             }
           }
+#pragma unroll
+          for (int u = 0; u < kBmUnroll; ++u) { doc[u] = ndoc[u]; v[u] = nv[u]; }
+          e = en;
         }
-        e += (long long)kBmUnroll * kBmThreads;
       }
     }
     __syncthreads();

@@ -745,25 +745,20 @@ __global__ void __launch_bounds__(256) seed_tau_kernel(const float* __restrict__
   const float* r = scores + (long long)row * ld;
   u32 prefix = 0, pmask = 0;
   int need = (int)kth;
-  if (g_hpar) {  // best finite sampled score: the upper end of the row's histogram range
-    if (tid == 0) s_max = 0u;
-    __syncthreads();
-    u32 mx = 0u;
-    for (int i = tid; i < m; i += 256) {
-      const u32 o = ord32(r[i]);
-      if (o <= 0xFF7FFFFFu && o > mx) mx = o;
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) { const u32 a = __shfl_xor_sync(0xffffffffu, mx, off); mx = a > mx ? a : mx; }
-    if (lane == 0) atomicMax(&s_max, mx);
-    __syncthreads();
-  }
+  if (tid == 0) s_max = 0u;
+  u32 mx = 0u;  // best finite sampled score (upper end of the row's histogram range): found in pass 1
   for (int shift = 24; shift >= 0; shift -= 8) {
     hist[tid] = 0;
     __syncthreads();
     for (int i = tid; i < m; i += 256) {
       const u32 o = ord32(r[i]);
+      if (shift == 24 && o <= 0xFF7FFFFFu && o > mx) mx = o;
       if ((o & pmask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+    }
+    if (shift == 24) {
+#pragma unroll
+      for (int off = 16; off; off >>= 1) { const u32 a = __shfl_xor_sync(0xffffffffu, mx, off); mx = a > mx ? a : mx; }
+      if (lane == 0) atomicMax(&s_max, mx);
     }
     __syncthreads();
     if (tid < 32) {
