@@ -500,7 +500,7 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
 static void bm25_plan(long long Bq, long long N, int k, int* S, int* C, size_t* off_counts, size_t* total) {
   const int sms = device_sm_count();
   const long long rows = Bq > 0 ? Bq : 1;
-  long long s = (2LL * sms + rows - 1) / rows;  // two 512-thread blocks per SM
+  long long s = ((long long)kBmBlocksPerSm * sms + rows - 1) / rows;  // blocks resident per SM
   const long long chunks = (N + kBmChunk - 1) / kBmChunk;
   if (s > chunks) s = chunks;
   if (s > 1024) s = 1024;  // finalize: kFinMaxStreams

@@ -591,7 +591,8 @@ int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const _
 //                         evaluates sparse / dense as a multiplication by the reciprocal)
 //                         -- the reference's per-query arithmetic does not depend on the query, so
 //                         it is done once; a query then only sums its terms' posting values.
-//   bm25_topk_kernel    : block = (doc split, query).  The split is walked in chunks of kBmChunk
+//   bm25_topk_kernel    : block = (doc split, query), 256 threads, 5 blocks per SM (independent barrier
+//                         domains hide each other's latency).  The split is walked in chunks of kBmChunk
 //                         docs whose float64 score accumulators live in shared memory; the query's
 //                         terms are applied one after the other (fixed order -> deterministic sums),
 //                         each by streaming the term's postings from a per-term cursor until the
@@ -624,7 +625,6 @@ int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, cons
   return (int)cudaGetLastError();
 }
 
-constexpr int kBmThreads = 512;
 constexpr int kBmUnroll = 4;      // postings per thread and iteration (memory-level parallelism)
 constexpr int kBmScan = kBmSlack;  // accumulators ranked between two prune checks
 

@@ -120,7 +120,16 @@ int launch_override_dense(const float* scores, long long ld, int B, long long N,
                           u32* ovr_lo, cudaStream_t st);
 
 // BM25 (ccr_kernels.cu)
-constexpr int kBmChunk = 8192;     // docs per shared-memory accumulator pass (64 KB of float64)
+// block shape, measured at the NQ shape (profiles/r01_bm25_bench.json): 4096 docs x 256 threads x 5 blocks
+// per SM 45.3 ms per 3,452 queries; 8192 x 512 x 2: 56.7 ms; 4096 x 512 x 2: 70.9; 8192 x 256 x 3: 65.7
+#ifndef CCR_BM_CHUNK
+#define CCR_BM_CHUNK 4096
+#define CCR_BM_THREADS 256
+#define CCR_BM_BLOCKS_PER_SM 5
+#endif
+constexpr int kBmChunk = CCR_BM_CHUNK;     // docs per shared-memory accumulator pass (8 bytes each)
+constexpr int kBmThreads = CCR_BM_THREADS;
+constexpr int kBmBlocksPerSm = CCR_BM_BLOCKS_PER_SM;
 constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query
 constexpr int kBmSlack = 1024;     // accumulators ranked between two prune checks
 int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,

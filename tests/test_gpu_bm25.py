@@ -93,7 +93,7 @@ def test_bm25_topk_vs_oracle(n, q, k, ccr):
 
 
 def test_bm25_dense_scores_vs_oracle_many_chunks(ccr):
-    """n_docs spanning several 8192-doc accumulator chunks and doc splits; long postings lists."""
+    """n_docs spanning many 4096-doc accumulator chunks and doc splits; long postings lists."""
     corpus, queries = _synthetic(5, 70000, 12, vocab=500, doc_len=30)
     model = ccr.BM25().fit(corpus)
     ref = O.BM25Ref().fit(corpus)
