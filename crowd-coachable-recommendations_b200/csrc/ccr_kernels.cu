@@ -456,31 +456,48 @@ __device__ __forceinline__ bool precedes(double sa, long long ia, double sb, lon
   return (sa > sb) || (sa == sb && ia < ib);
 }
 
-__global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restrict__ s,
-                                                         const long long* __restrict__ ids, int G,
-                                                         long long B, int k_in, int k_out, float* os,
-                                                         double* os64, long long* oi) {
+// kStaged: the row's G runs are first copied to shared memory (16 bytes per entry) so that the
+// ~G * log2(k) probes of every entry are shared-memory reads; otherwise they go to global memory.
+template <bool kStaged>
+__global__ void __launch_bounds__(1024) merge_topk_kernel(const double* __restrict__ s,
+                                                          const long long* __restrict__ ids, int G,
+                                                          long long B, int k_in, int k_out, float* os,
+                                                          double* os64, long long* oi) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
   const long long row = blockIdx.x;
+  const int n = G * k_in;
+  double* l_s = reinterpret_cast<double*>(merge_smem);            // [G][k_in] (staged only)
+  long long* l_id = reinterpret_cast<long long*>(l_s + n);        // [G][k_in]
   __shared__ int s_valid;
   if (threadIdx.x == 0) s_valid = 0;
+  if (kStaged) {
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      const int g = e / k_in, i = e - g * k_in;
+      const long long off = ((long long)g * B + row) * k_in + i;
+      l_s[e] = s[off];
+      l_id[e] = ids[off];
+    }
+  }
   __syncthreads();
   int local_valid = 0;
-  for (int e = threadIdx.x; e < G * k_in; e += blockDim.x) {
+  for (int e = threadIdx.x; e < n; e += blockDim.x) {
     const int g = e / k_in, i = e - g * k_in;
     const long long off = ((long long)g * B + row) * k_in;
-    const long long id = ids[off + i];
+    const long long id = kStaged ? l_id[e] : ids[off + i];
     if (id < 0) continue;
     ++local_valid;
-    const double sc = s[off + i];
+    const double sc = kStaged ? l_s[e] : s[off + i];
     int rank = 0;
-    for (int h = 0; h < G; ++h) {
+    for (int h = 0; h < G && rank < k_out; ++h) {
       const long long oh = ((long long)h * B + row) * k_in;
-      // number of valid entries of run h that precede (sc, id)
-      int lo = 0, hi = k_in;
+      // number of valid entries of run h that precede (sc, id); more than k_out - rank of them
+      // would push the entry out of the result anyway, so the search stops there
+      int lo = 0, hi = k_in < k_out - rank ? k_in : k_out - rank;
       while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        long long mid_id = ids[oh + mid];
-        bool before = (mid_id >= 0) && precedes(s[oh + mid], mid_id, sc, id);
+        const int mid = (lo + hi) >> 1;
+        const long long mid_id = kStaged ? l_id[h * k_in + mid] : ids[oh + mid];
+        const double mid_s = kStaged ? l_s[h * k_in + mid] : s[oh + mid];
+        const bool before = (mid_id >= 0) && precedes(mid_s, mid_id, sc, id);
         if (before) lo = mid + 1; else hi = mid;
       }
       rank += lo;
@@ -505,7 +522,15 @@ __global__ void __launch_bounds__(256) merge_topk_kernel(const double* __restric
 int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,
                       float* os, double* os64, long long* oi, cudaStream_t st) {
   if (B == 0) return 0;
-  merge_topk_kernel<<<(unsigned)B, 256, 0, st>>>(s, ids, G, B, k_in, k_out, os, os64, oi);
+  const size_t smem = (size_t)G * k_in * 16;
+  if (smem <= 200 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = G * k_in >= 4096 ? 1024 : 256;
+    merge_topk_kernel<true><<<(unsigned)B, threads, smem, st>>>(s, ids, G, B, k_in, k_out, os, os64, oi);
+  } else {
+    merge_topk_kernel<false><<<(unsigned)B, 256, 0, st>>>(s, ids, G, B, k_in, k_out, os, os64, oi);
+  }
   return (int)cudaGetLastError();
 }
 

@@ -164,14 +164,15 @@ def test_evaluate_item_rec_metrics(ccr, golden_dir):
     assert abs(m["obj_mean"] - want["obj_mean"]) / abs(want["obj_mean"]) < RTOL
 
 
-def test_merge_topk_matches_oracle(ccr):
+@pytest.mark.parametrize("G,B,k", [(4, 37, 20), (8, 48, 1000), (2, 5, 2048), (8, 3, 2048)])
+def test_merge_topk_matches_oracle(ccr, G, B, k):
+    """(8, 3, 2048) exceeds the shared-memory staging of the merge and takes the global-memory path."""
     dev = torch.device("cuda:0")
     rs = np.random.RandomState(3)
-    G, B, k = 4, 37, 20
     sc = np.sort(rs.standard_normal((G, B, k)), axis=2)[:, :, ::-1].copy()
-    sc[1, :, 10:] = sc[0, :, 10:]  # cross-run ties
+    sc[1, :, k // 2:] = sc[0, :, k // 2:]  # cross-run ties
     ids = rs.permutation(G * B * k).reshape(G, B, k).astype(np.int64)
-    ids[3, :, 15:] = -1  # padding
+    ids[G - 1, :, 3 * k // 4:] = -1  # padding
     s, i, d = ccr.merge_topk(torch.as_tensor(sc).to(dev), torch.as_tensor(ids).to(dev), k)
     for b in range(B):
         ent = [(-sc[g_, b, j], ids[g_, b, j]) for g_ in range(G) for j in range(k) if ids[g_, b, j] >= 0]
