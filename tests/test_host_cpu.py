@@ -165,3 +165,26 @@ def test_sparse_mask_from_flat_equals_from_lists(monkeypatch):
     assert a.max_row_nnz == b.max_row_nnz and b.n_rows == 41
     with pytest.raises(IndexError):
         engine.SparseMask.from_flat([1], [50], 50, -1e6, engine.MASK_SET, "cpu")
+
+
+def test_expression_recognition_factor_vs_materialised():
+    """Which expressions go to the fused kernel (factor pair), which to the dense top-k
+    (materialised matrix), which are refused -- host-side logic only."""
+    import scipy.sparse as sps
+
+    import ccr_b200 as ccr
+
+    U, V = np.ones((3, 8), np.float32), np.ones((5, 8), np.float32)
+    prior = sps.csr_matrix(([1.0], ([0], [1])), shape=(3, 5))
+    mm = ccr.LazyDenseMatrix(U) @ ccr.LazyDenseMatrix(V).T
+    dense = ccr.LazyDenseMatrix(np.ones((3, 5), np.float32))
+    assert ccr.fused_plan(mm) is not None and ccr.dense_plan(mm) is None
+    assert ccr.fused_plan(mm + prior).sparse.nnz == 1 and ccr.fused_plan(mm - prior).sparse[0, 1] == -1.0
+    assert ccr.fused_plan(dense) is None and ccr.dense_plan(dense) is not None
+    p = ccr.dense_plan(dense + prior - prior * 2.0) if hasattr(prior, "__mul__") else None
+    assert p is not None and p.sparse[0, 1] == -1.0 and p.shape == (3, 5)
+    assert ccr.dense_plan(dense + dense) is None and ccr.fused_plan(mm + mm) is None   # two dense terms
+    assert ccr.dense_plan(dense.exp()) is None and ccr.fused_plan(mm.exp()) is None    # non-linear
+    assert ccr.dense_plan(ccr.auto_cast_lazy_score(np.zeros((2, 2)))) is not None      # plain ndarray
+    with pytest.raises(RuntimeError, match="CUDA"):                                      # no CPU path behind it
+        ccr._assign_topk(dense, 2)
