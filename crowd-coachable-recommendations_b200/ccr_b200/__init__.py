@@ -35,6 +35,7 @@ from .ranking import (  # noqa: F401
     generate_embeddings_device,
     mrr_at_k,
     ranking,
+    ranking_sharded,
     ranking_tensors,
 )
 from .dist import ShardedIndex, shard_bounds  # noqa: F401

@@ -138,3 +138,43 @@ def mrr_at_k(order, corpus_ids, queries_ids, qrels, k_values=(1, 5, 10, 100)):
             if hit.size:
                 first[qi] = hit[0] + 1
     return {f"MRR@{k}": round(float(np.mean(np.where(first <= k, 1.0 / first, 0.0))), 5) for k in k_values}
+
+
+def ranking_sharded(corpus, queries, embedding_func, batch_size, block_dict=None, group=None, device=None,
+                    index_cls=None):
+    """``ranking`` with the passage table row-sharded over the ranks of a torch.distributed group
+    (one process per GPU): every rank encodes the queries and ONLY its own contiguous slice of the
+    corpus (``shard_bounds``) straight into its device shard -- the encoder pass, which dominates the
+    reference's wall clock, is split G ways and no rank ever holds the whole table -- then the
+    fused local top-k, one all-gather and the G-way merge produce the global result.  Every rank
+    returns the same ``{qid: {pid: score}}`` as the single-table call."""
+    from .dist import ShardedIndex
+
+    sim = os.environ["CCREC_SIM_TYPE"]  # KeyError when unset, like ms_marco_eval.py:212
+    normalize = sim == "cos"
+    queries_ids, corpus_ids = list(queries.keys()), list(corpus.keys())
+    if len(queries_ids) == 0:
+        return {}
+    with torch.no_grad():
+        q_emb = torch.cat([torch.as_tensor(embedding_func([queries[i] for i in queries_ids[s:s + batch_size]]))
+                           for s in range(0, len(queries_ids), batch_size)])
+        index = (index_cls or ShardedIndex)(len(corpus_ids), q_emb.shape[1], normalize=normalize, device=device,
+                                            group=group)
+        for s in range(index.lo, index.hi, batch_size):
+            e = min(index.hi, s + batch_size)
+            index.add_local(torch.as_tensor(embedding_func([corpus[i] for i in corpus_ids[s:e]])))
+    mask = None
+    if block_dict is not None:
+        print("using block_dict")
+        mask = build_block_mask(queries_ids, corpus_ids, block_dict, index.device)
+    k = min(RANKING_TOPN, len(corpus_ids))
+    scores = np.empty((len(queries_ids), k), dtype=np.float32)
+    order = np.empty((len(queries_ids), k), dtype=np.int64)
+    for s in range(0, len(queries_ids), QUERY_CHUNK):
+        e = min(len(queries_ids), s + QUERY_CHUNK)
+        sc, ids, _ = index.search(q_emb[s:e], k, mask=mask.rows(s, e) if mask is not None else None)
+        scores[s:e] = sc.cpu().numpy()
+        order[s:e] = ids.cpu().numpy()
+    corpus_arr = np.asarray(corpus_ids, dtype=object)
+    return {qid: dict(zip(corpus_arr[order[step]].tolist(), scores[step].tolist()))
+            for step, qid in enumerate(queries_ids)}
