@@ -26,7 +26,7 @@ from .score_array import (  # noqa: F401
     get_batch_size,
     score_op,
 )
-from .util import _argsort, _assign_topk, argsort, assign_topk, topk_lazy  # noqa: F401
+from .util import _argsort, _assign_topk, argsort, assign_topk, topk_lazy, transform_scores  # noqa: F401
 from .metrics import evaluate_assigned, evaluate_item_rec  # noqa: F401
 from .ranking import (  # noqa: F401
     build_block_mask,

@@ -155,3 +155,23 @@ def _argsort(S, tie_breaker=1e-10, device="cpu"):
 
 
 argsort = _argsort
+
+
+def transform_scores(all_emb, i_to_ptr, j_to_ptr, sim_type=None):
+    """The users x items score matrix of ``BertBPR.transform`` (src/ccrec/models/bbpr.py:528-550) as a
+    lazy factor pair instead of a dense host matrix: ``all_emb[i_to_ptr] @ all_emb[j_to_ptr].T``, with
+    both sides L2-normalised first (``F.normalize``, eps 1e-12) when CCREC_SIM_TYPE is ``cos``.
+    ``+ D.prior_score``, ``_assign_topk`` and ``evaluate_item_rec`` then run through the fused kernel;
+    nothing of size users x items is ever materialised."""
+    import os
+
+    from .score_array import LazyDenseMatrix
+
+    if sim_type is None:
+        sim_type = os.environ["CCREC_SIM_TYPE"]  # KeyError when unset, like bbpr.py:538
+    emb = torch.as_tensor(all_emb).detach().float().cpu()
+    users, items = emb[torch.as_tensor(np.asarray(i_to_ptr))], emb[torch.as_tensor(np.asarray(j_to_ptr))]
+    if sim_type == "cos":
+        users = torch.nn.functional.normalize(users, p=2, dim=1)
+        items = torch.nn.functional.normalize(items, p=2, dim=1)
+    return LazyDenseMatrix(users.numpy()) @ LazyDenseMatrix(items.numpy()).T

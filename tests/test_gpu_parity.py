@@ -403,3 +403,19 @@ def test_topk_dense_abi_matches_float64_sort(ccr, B, N, k, mode):
     np.testing.assert_array_equal(s.cpu().numpy(), want_v[:, :k].float().numpy())
     with pytest.raises(RuntimeError, match="out of range"):
         ccr.topk_dense(torch.zeros(2, 3, device=dev), 4)
+
+
+@pytest.mark.parametrize("sim", ["dot", "cos"])
+def test_transform_scores_topk_vs_reference_matrix(ccr, sim):
+    """bbpr.py:528-550 replaced by the lazy factor pair: top-k (+ prior) through the fused kernel
+    against the reference's dense matrix path under the tolerance rule."""
+    rs = np.random.RandomState(8)
+    all_emb = cases.embeddings(77, 900, 64, clustered=(sim == "cos"))
+    i_to_ptr, j_to_ptr = rs.randint(0, 900, size=33), rs.permutation(900)[:700]
+    prior = sps.csr_matrix((np.full(33, -1e10), (np.arange(33), rs.randint(0, 700, size=33))), shape=(33, 700))
+    S = ccr.transform_scores(all_emb, i_to_ptr, j_to_ptr, sim_type=sim) + prior
+    got = ccr._assign_topk(S, 10).indices.reshape(33, 10)
+    dense = O.transform_scores_ref(all_emb, i_to_ptr, j_to_ptr, 256, sim).double().numpy() + prior.toarray()
+    got_scores = np.take_along_axis(dense, got, 1)
+    errs = O.check_topk(got_scores, got, full_scores=dense, rtol=RTOL, atol=2e-3 if sim == "cos" else 1e-4)
+    assert not errs, errs[:3]

@@ -188,3 +188,19 @@ def test_expression_recognition_factor_vs_materialised():
     assert ccr.dense_plan(ccr.auto_cast_lazy_score(np.zeros((2, 2)))) is not None      # plain ndarray
     with pytest.raises(RuntimeError, match="CUDA"):                                      # no CPU path behind it
         ccr._assign_topk(dense, 2)
+
+
+@pytest.mark.parametrize("sim", ["dot", "cos"])
+def test_transform_scores_factor_pair_equals_reference_matrix(sim):
+    """bbpr.py:528-550 as a lazy factor pair: its product is the reference's dense matrix."""
+    import ccr_b200 as ccr
+    from oracle import ccr_oracle as O
+
+    rs = np.random.RandomState(4)
+    all_emb = rs.standard_normal((60, 16)).astype(np.float32)
+    i_to_ptr, j_to_ptr = rs.randint(0, 60, size=9), rs.permutation(60)[:41]
+    S = ccr.transform_scores(all_emb, i_to_ptr, j_to_ptr, sim_type=sim)
+    assert S.shape == (9, 41) and ccr.fused_plan(S) is not None
+    want = O.transform_scores_ref(all_emb, i_to_ptr, j_to_ptr, 16, sim).numpy()
+    np.testing.assert_allclose(S.left.c @ S.right.c, want, rtol=1e-5, atol=1e-5)
+    assert ccr.fused_plan(S[2:5]).shape == (3, 41)  # row slicing keeps the factor form
