@@ -120,6 +120,40 @@ def write_requests(working_dir, header, rows, id_track, n_repeats, repeat_seed):
     return request_orig, request_perm
 
 
+def generate_train_data(qids, qrels, ranking_profile, ranking_profile_2, corpus_key_list=(), rng_seed=None):
+    """Oracle-labelled training tasks of the notebook loop (scripts/al_oracle_agent.py:134-180): per
+    query the dense top-2, then BM25 passages up to four candidates -- or, with ``corpus_key_list``, up
+    to three plus one random corpus passage as attention check (``RandomState(rng_seed)``, one
+    ``choice`` per attempt) -- shuffled with the global ``random`` module exactly once per query like
+    the reference; a candidate listed in ``qrels[qid]`` becomes the positive (the last one if several),
+    the others negatives; queries without a labelled candidate are skipped in the attention-check
+    variant and keep the shuffled head as positive otherwise."""
+    import random
+
+    rng = np.random.RandomState(rng_seed)
+    train_data = {}
+    for qid in qids:
+        pids = list(ranking_profile[qid].keys())[:2]
+        for pid in ranking_profile_2[qid].keys():
+            if len(pids) == 4:
+                break
+            if pid not in pids:
+                pids.append(pid)
+        if len(corpus_key_list):
+            pids = pids[:3]
+            while len(pids) < 4:
+                pid = corpus_key_list[rng.choice(len(corpus_key_list))]
+                if pid not in pids:
+                    pids.append(pid)
+        random.shuffle(pids)
+        labelled = [pid for pid in pids if pid in qrels[qid]]
+        if labelled:
+            train_data[qid] = {"pos_pid": [labelled[-1]], "neg_pid": [pid for pid in pids if pid not in qrels[qid]]}
+        elif not len(corpus_key_list):
+            train_data[qid] = {"pos_pid": pids[:1], "neg_pid": pids[1:]}
+    return train_data
+
+
 def rank_step(corpus, queries, qrels, embedding_func, results_dir, step, ranking_profile_bm25, qids_split,
               n_repeats=3, repeat_seed=42, number_of_qid_split_batch=None, block_dict=None, landing_image=None,
               batch_size=512, device="cuda"):

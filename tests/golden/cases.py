@@ -200,3 +200,18 @@ AL0_CASES = {
     "pantry_like_step5": dict(seed=52, n=6, q=6, depth=3, text_len=300, splits=4, step=5, n_repeats=2,
                               repeat_seed=7, queries_are_corpus=True, images=True),
 }
+
+
+def al0_qrels(c):
+    """qrels for an al0 case: for two queries in three the relevant passage is one of the dense
+    top-3 or BM25 top-3 (so it is usually among the candidates), otherwise an unrelated one."""
+    rs = np.random.RandomState(99)
+    pids = list(c["corpus"])
+    out = {}
+    for n, qid in enumerate(c["queries"]):
+        pool = list(c["ranking_profile"][qid])[:3] + list(c["ranking_profile_bm25"][qid])[:3]
+        rel = pool[rs.randint(len(pool))] if n % 3 else pids[rs.randint(len(pids))]
+        out[qid] = {rel: 1}
+        if n % 5 == 0:
+            out[qid][pool[0]] = 1  # two labelled candidates: the later one in shuffled order wins
+    return out

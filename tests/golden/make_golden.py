@@ -127,7 +127,25 @@ def make_al0():
             orig = open(os.path.join(tmp, "request_orig.csv"), "rb").read()
             perm = open(os.path.join(tmp, "request_perm.csv"), "rb").read()
             track = torch.load(os.path.join(tmp, "id_track.pt"))
+        # scripts/al_oracle_agent.py:134-180 (generate_train_data): the module cannot be imported
+        # (encoder / lightning imports, module-level work), so the function's own source text is executed
+        import random
+
+        agent = open(os.path.join(_ref_loader.REFERENCE_ROOT, "scripts", "al_oracle_agent.py")).read()
+        fn_src = agent[agent.index("def generate_train_data("):agent.index("def combine_train_data(")]
+        ns2 = dict(np=np, random=random)
+        exec(compile(fn_src, "al_oracle_agent.py[generate_train_data]", "exec"), ns2)
+        qrels = cases.al0_qrels(c)
+        qids = c["qids_split"][c["step"] % c["number_of_qid_split_batch"]]
+        train = {}
+        for variant, keys in (("plain", []), ("attention", list(c["corpus"].keys()))):
+            random.seed(1234)
+            train[variant] = ns2["generate_train_data"](qids, qrels, c["ranking_profile"], c["ranking_profile_bm25"],
+                                                        keys, c["step"])
+        import json
+
         np.savez_compressed(os.path.join(HERE, f"al0_{name}.npz"), request_orig=np.frombuffer(orig, dtype=np.uint8),
+                            train_data=np.array(json.dumps(train, sort_keys=True)),
                             request_perm=np.frombuffer(perm, dtype=np.uint8),
                             id_track_keys=np.array(list(track.keys()), dtype=object).astype(str),
                             id_track_vals=np.array(list(track.values()), dtype=object).astype(str))

@@ -82,3 +82,24 @@ def test_mrr_from_profile_follows_beir_semantics():
     m = al_rank.mrr_from_profile(qrels, prof, (1, 2, 3))
     # q0: first hit at rank 2; q1: ordered c, b, a -> rank 3; q2: none; divided by len(qrels) = 4
     assert m == {"MRR@1": 0.0, "MRR@2": round(0.5 / 4, 5), "MRR@3": round((0.5 + 1 / 3) / 4, 5)}
+
+
+@pytest.mark.parametrize("name", list(cases.AL0_CASES))
+def test_generate_train_data_matches_reference(name, golden_dir):
+    """scripts/al_oracle_agent.py:134-180 (function source executed for the golden) vs the drop-in:
+    same candidates, same shuffle (global ``random``, seeded here), same positive / negative split."""
+    import json
+    import random
+
+    from ccr_b200 import al_rank
+
+    g = np.load(os.path.join(golden_dir, f"al0_{name}.npz"))
+    want = json.loads(str(g["train_data"]))
+    c = cases.al0_case(name)
+    qrels = cases.al0_qrels(c)
+    qids = c["qids_split"][c["step"] % c["number_of_qid_split_batch"]]
+    for variant, keys in (("plain", []), ("attention", list(c["corpus"].keys()))):
+        random.seed(1234)
+        got = al_rank.generate_train_data(qids, qrels, c["ranking_profile"], c["ranking_profile_bm25"], keys, c["step"])
+        assert got == want[variant], variant
+        assert list(got.keys()) == [q for q in qids if q in want[variant]]
