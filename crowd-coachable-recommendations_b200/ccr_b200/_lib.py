@@ -12,8 +12,9 @@ LIB_PATH = os.environ.get("CCR_B200_LIB") or os.path.join(os.path.dirname(_HERE)
 MASK_NONE, MASK_SET, MASK_ADD = 0, 1, 2
 ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 FLAG_ALLOW_SHORT = 0x10
+FLAG_PACKED_KEYS = 0x20
 MAX_K = 2048
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, EK_RANGE = 0, -1, -2, -3, -4, -5
 
@@ -24,12 +25,16 @@ EXPORTS = [
     "ccr_score_topk_bf16",
     "ccr_score_topk_workspace_bytes",
     "ccr_merge_topk",
+    "ccr_merge_topk_keys",
+    "ccr_mask_column_shard",
     "ccr_ingest_rows_f32",
     "ccr_normalize_rows_bf16",
     "ccr_score_dense_f32",
     "ccr_choose_algo",
     "ccr_plan_info",
     "ccr_set_profile_events",
+    "ccr_set_status_record",
+    "ccr_debug_reload_env",
     "ccr_topk_dense_workspace_bytes",
     "ccr_topk_dense_f32",
     "ccr_bm25_build_impacts",
@@ -70,6 +75,10 @@ def lib():
     L.ccr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32, i64, i64, i32]
     L.ccr_merge_topk.restype = i32
     L.ccr_merge_topk.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
+    L.ccr_merge_topk_keys.restype = i32
+    L.ccr_merge_topk_keys.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp]
+    L.ccr_mask_column_shard.restype = i32
+    L.ccr_mask_column_shard.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]
     L.ccr_ingest_rows_f32.restype = i32
     L.ccr_ingest_rows_f32.argtypes = [vp, i64, i32, i64, vp, i64, i32, vp]
     L.ccr_normalize_rows_bf16.restype = i32
@@ -81,7 +90,11 @@ def lib():
     L.ccr_set_profile_events.restype = None
     L.ccr_set_profile_events.argtypes = [vp, vp]
     L.ccr_plan_info.restype = i32
-    L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i32, c.POINTER(c.c_int32)]
+    L.ccr_plan_info.argtypes = [i64, i64, i32, i32, i64, i64, i32, c.POINTER(c.c_int32)]
+    L.ccr_set_status_record.restype = None
+    L.ccr_set_status_record.argtypes = [vp]
+    L.ccr_debug_reload_env.restype = None
+    L.ccr_debug_reload_env.argtypes = []
     f64 = c.c_double
     L.ccr_topk_dense_workspace_bytes.restype = sz
     L.ccr_topk_dense_workspace_bytes.argtypes = [i64, i64, i32, i64, i64]
@@ -111,7 +124,13 @@ def check(rc):
         raise CcrError(rc, msg)
 
 
-def plan_info(B, n_items, D, k, flags=0):
-    arr = (ctypes.c_int32 * 4)()
-    check(lib().ccr_plan_info(B, n_items, D, k, flags, arr))
-    return {"n_q_tiles": arr[0], "n_splits": arr[1], "cand_capacity": arr[2], "algo": arr[3]}
+def plan_info(B, n_items, D, k, flags=0, mask_nnz=0, mask_max_row_nnz=-1):
+    arr = (ctypes.c_int32 * 8)()
+    check(lib().ccr_plan_info(B, n_items, D, k, mask_nnz, mask_max_row_nnz, flags, arr))
+    return {"n_q_tiles": arr[0], "n_splits": arr[1], "cand_capacity": arr[2], "algo": arr[3], "two_cta": arr[4],
+            "seed_items": arr[5], "n_kernel_launches": arr[6], "prefetch_tiles": arr[7]}
+
+
+def reload_env():
+    """Diagnostics: make libccr_b200 re-read the CCR_* knobs after os.environ was changed."""
+    lib().ccr_debug_reload_env()

@@ -21,18 +21,23 @@ def _stream_ptr(device):
 
 
 class _Workspace:
-    """Per-device scratch that only grows; owned by the caller side of the ABI."""
+    """Scratch that only grows, one buffer per (device, stream): calls on different streams (or from
+    threads that use different streams) never share candidate / threshold state.  Calls issued on one
+    stream are ordered by it, so they may reuse the buffer.  Owned by the caller side of the ABI."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, device, nbytes):
-        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        key = (device.type, index, torch.cuda.current_stream(device).cuda_stream)
         b = self._buf.get(key)
         if b is None or b.numel() < nbytes:
             b = None
             self._buf[key] = None
             b = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+            # the old block may still be in use by work queued on this stream; the caching allocator
+            # only recycles it for the same stream, i.e. after that work
             self._buf[key] = b
         return b
 
@@ -42,6 +47,36 @@ class _Workspace:
 
 workspace = _Workspace()
 
+_status_record = None
+
+
+def _status():
+    """Host-mapped watchdog record shared with the library (ccr_set_status_record): readable after a
+    device trap has poisoned the context."""
+    global _status_record
+    if _status_record is None:
+        _status_record = torch.zeros(4, dtype=torch.int32).pin_memory()
+        _lib.lib().ccr_set_status_record(_status_record.data_ptr())
+    return _status_record
+
+
+def device_status():
+    """{code, where, block, extra} written by the kernels' bounded barrier waits (code 0 = ok)."""
+    c, w, b, x = (int(v) for v in _status())
+    return {"code": c, "where": w, "block": b, "extra": x}
+
+
+def synchronize(device=None):
+    """torch.cuda.synchronize that decodes the watchdog record when the device reports a failure."""
+    try:
+        torch.cuda.synchronize(device)
+    except RuntimeError as e:
+        st = device_status()
+        if st["code"]:
+            raise RuntimeError(f"libccr_b200 watchdog: barrier wait timed out (where={st['where']}, "
+                               f"block={st['block']}, parity={st['extra']}); CUDA said: {e}") from e
+        raise
+
 
 class SparseMask:
     """Device CSR over item columns: the history / block mask and additive priors.
@@ -50,6 +85,8 @@ class SparseMask:
     MASK_ADD: value added in float64 (rime_lite prior_score, src/rime_lite/dataset/base.py:234,279-282).
     Columns are sorted and unique per row (duplicates: summed for ADD, collapsed for SET).
     """
+
+    _f32_exact = None
 
     def __init__(self, indptr, cols, vals, n_cols, mode, device):
         self.n_rows = len(indptr) - 1
@@ -72,19 +109,33 @@ class SparseMask:
 
 
     @classmethod
-    def from_device_tensors(cls, indptr, cols, vals, host, n_cols, mode):
+    def from_device_tensors(cls, indptr, cols, vals, host, n_cols, mode, nnz=None, max_row_nnz=None,
+                            f32_exact=None):
         """Wrap CSR arrays that are already (being copied) on the device; ``host`` holds the same
-        arrays as numpy for the host-side slicing helpers."""
+        arrays as numpy for the host-side slicing helpers, or is None for a CSR that only exists on
+        the device -- then ``nnz`` / ``max_row_nnz`` are upper bounds (the C ABI accepts bounds)."""
         self = cls.__new__(cls)
         self.n_rows = int(indptr.shape[0]) - 1
         self.n_cols = int(n_cols)
         self.mode = mode
         self.host = host
-        self.nnz = int(host[0][-1])
-        self.max_row_nnz = int(np.diff(host[0]).max()) if self.n_rows else 0
+        self.nnz = int(host[0][-1]) if nnz is None else int(nnz)
+        if max_row_nnz is None:
+            max_row_nnz = int(np.diff(host[0]).max()) if self.n_rows else 0
+        self.max_row_nnz = int(max_row_nnz)
         self.device = indptr.device
         self.indptr, self.cols, self.vals = indptr, cols, vals
+        self._f32_exact = f32_exact
         return self
+
+    @property
+    def f32_exact(self):
+        """True when ranking by float32 keys is exact for this mask: SET mode with values that are
+        float32 numbers (-1e6 is).  ADD priors are summed in float64 and never qualify."""
+        if self._f32_exact is None:
+            v = self.host[2]
+            self._f32_exact = bool(self.mode == MASK_SET and np.array_equal(v.astype(np.float32).astype(np.float64), v))
+        return self._f32_exact
 
     @classmethod
     def from_scipy(cls, csr, mode, device):
@@ -140,6 +191,22 @@ class SparseMask:
         a, b = ip[start], ip[stop]
         return SparseMask(ip[start : stop + 1] - a, c[a:b], v[a:b], self.n_cols, self.mode, self.device)
 
+    def column_shard_device(self, lo, hi):
+        """column_shard on the device (C ABI: ccr_mask_column_shard): no host pass, no upload.  The
+        shard's entry count stays on the device; nnz / max_row_nnz of the result are upper bounds."""
+        _require_cuda(self.indptr, "mask")
+        dev = self.indptr.device
+        out_ip = torch.empty_like(self.indptr)
+        out_c = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        out_v = torch.empty(max(self.nnz, 1), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ccr_mask_column_shard(self.indptr.data_ptr(), self.cols.data_ptr() if self.nnz else None,
+                                                  self.vals.data_ptr() if self.nnz else None, self.n_rows, int(lo), int(hi),
+                                                  out_ip.data_ptr(), out_c.data_ptr(), out_v.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc)
+        return SparseMask.from_device_tensors(out_ip, out_c, out_v, None, hi - lo, self.mode, nnz=self.nnz,
+                                              max_row_nnz=self.max_row_nnz, f32_exact=self.f32_exact)
+
     def column_shard(self, lo, hi):
         """Entries with lo <= col < hi, re-based to local column ids (row-sharded tables)."""
         ip, c, v = self.host
@@ -151,12 +218,13 @@ class SparseMask:
 
 
 def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_lib.ALGO_AUTO,
-               allow_short=False, want_f64=False, n_items=None, D=None):
+               allow_short=False, want_f64=False, n_items=None, D=None, want_keys=False):
     """Fused ``topk(q @ items.T [mask], k)`` on the device (C ABI: ccr_score_topk_bf16).
 
     q [B, ldq] bf16 cuda, items [N, ldi] bf16 cuda (row-major, last dim contiguous).
     Returns (scores float32 [B,k] descending, ids int64 [B,k]) and, with ``want_f64``, the
-    float64 values the order was decided on.
+    float64 values the order was decided on; with ``want_keys`` instead the packed uint64
+    exchange keys (CCR_FLAG_PACKED_KEYS; int64 tensor holding the bit pattern).
     """
     _require_cuda(q, "q")
     _require_cuda(items, "items")
@@ -172,6 +240,10 @@ def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_l
     ldi = items.stride(0) if items.shape[0] > 1 else max(items.stride(0), items.shape[1])
     k = int(k)
     flags = int(algo) | (_lib.FLAG_ALLOW_SHORT if allow_short else 0)
+    if want_keys:
+        if want_f64:
+            raise ValueError("want_keys and want_f64 are exclusive (one 8-byte slot per entry)")
+        flags |= _lib.FLAG_PACKED_KEYS
     L = _lib.lib()
     if mask is not None:
         if mask.n_rows != B:
@@ -182,6 +254,9 @@ def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_l
     out_s = torch.empty((B, k), dtype=torch.float32, device=dev)
     out_i = torch.empty((B, k), dtype=torch.int64, device=dev)
     out_d = torch.empty((B, k), dtype=torch.float64, device=dev) if want_f64 else None
+    if want_keys:
+        out_d = torch.empty((B, k), dtype=torch.int64, device=dev)
+    _status()
     with torch.cuda.device(dev):
         hmax = mask.max_row_nnz if mask is not None else -1
         need = L.ccr_score_topk_workspace_bytes(B, N, D, k, nnz, hmax, flags)
@@ -195,10 +270,10 @@ def score_topk(q, items, k, mask: SparseMask | None = None, id_offset=0, algo=_l
             mask.cols.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
             mask.vals.data_ptr() if mask is not None and nnz else (mask.indptr.data_ptr() if mask is not None else None),
             nnz, hmax, mask.mode if mask is not None else MASK_NONE, int(id_offset),
-            out_s.data_ptr(), out_d.data_ptr() if want_f64 else None, out_i.data_ptr(),
+            out_s.data_ptr(), out_d.data_ptr() if out_d is not None else None, out_i.data_ptr(),
             ws.data_ptr(), ws.numel(), flags, _stream_ptr(dev))
     _lib.check(rc)
-    return (out_s, out_i, out_d) if want_f64 else (out_s, out_i)
+    return (out_s, out_i, out_d) if out_d is not None else (out_s, out_i)
 
 
 def merge_topk(scores64, ids, k_out):
@@ -216,6 +291,22 @@ def merge_topk(scores64, ids, k_out):
                                        out_d.data_ptr(), out_i.data_ptr(), _stream_ptr(dev))
     _lib.check(rc)
     return out_s, out_i, out_d
+
+
+def merge_topk_keys(keys, k_out):
+    """[G,B,k_in] packed exchange keys (int64 bit patterns) -> merged (scores f32, ids i64) [B,k_out]
+    (C ABI: ccr_merge_topk_keys)."""
+    _require_cuda(keys, "keys")
+    G, B, k_in = keys.shape
+    keys = keys.contiguous()
+    dev = keys.device
+    out_s = torch.empty((B, k_out), dtype=torch.float32, device=dev)
+    out_i = torch.empty((B, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ccr_merge_topk_keys(keys.data_ptr(), G, B, k_in, k_out, out_s.data_ptr(), out_i.data_ptr(),
+                                            _stream_ptr(dev))
+    _lib.check(rc)
+    return out_s, out_i
 
 
 def topk_dense(scores, k, mask: SparseMask | None = None):
@@ -257,6 +348,10 @@ def ingest_rows(src, dst, normalize=False):
     n, D = src.shape
     if dst.shape[0] != n or dst.shape[1] < D:
         raise ValueError("dst shape mismatch")
+    if n > 1 and dst.stride(0) != dst.shape[1]:
+        # the kernel zero-fills every column up to the row pitch: a column slice of a wider tensor
+        # would have its neighbours overwritten
+        raise ValueError("dst rows must be dense (stride(0) == shape[1])")
     ld_src = src.stride(0) if n > 1 else max(src.stride(0), D)
     ld_dst = dst.stride(0) if n > 1 else max(dst.stride(0), dst.shape[1])
     L = _lib.lib()

@@ -84,11 +84,13 @@ class EmbeddingTable:
         out = torch.empty((q.shape[0], self.ld), dtype=torch.bfloat16, device=self.device)
         return engine.ingest_rows(q, out, normalize=self.normalize)
 
-    def search(self, queries, k, mask=None, algo=0, allow_short=False, want_f64=False, encoded=False):
-        """Top-k of queries against the resident rows.  Returns (scores, global ids[, scores64])."""
+    def search(self, queries, k, mask=None, algo=0, allow_short=False, want_f64=False, encoded=False,
+               want_keys=False):
+        """Top-k of queries against the resident rows.  Returns (scores, global ids[, scores64 | keys])."""
         q = queries if encoded else self.encode_queries(queries)
         return engine.score_topk(q, self.data, k, mask=mask, id_offset=self.id_offset, algo=algo,
-                                 allow_short=allow_short, want_f64=want_f64, n_items=self.n, D=self.ld)
+                                 allow_short=allow_short, want_f64=want_f64, n_items=self.n, D=self.ld,
+                                 want_keys=want_keys)
 
     def dense_scores(self, queries, encoded=False):
         q = queries if encoded else self.encode_queries(queries)

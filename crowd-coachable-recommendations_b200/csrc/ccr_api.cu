@@ -4,14 +4,59 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/ccr_b200.h"
 #include "ccr_params.cuh"
 
 using namespace ccr;
 
 static thread_local char g_err[512] = "";
-static void* g_status_override = nullptr;  // diagnostics: host-mapped DeviceStatus (tests only)
+static void* g_status_record = nullptr;  // see ccr_set_status_record
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;  // see ccr_set_profile_events
+
+// Diagnostic knobs.  The environment is parsed ONCE, on first use; a test or A/B
+// harness that changes it inside a live process calls ccr_debug_reload_env().  None is needed in
+// production.
+namespace {
+struct Knobs {
+  int mask_exclude = 0, two_cta = -1, split_mult = 0, cap_mult = 0, no_share = 0, no_seed = 0, no_hist = 0;
+  long long seed_m = 0;
+  int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0, prefetch = -1;
+  float debug_tau = 0.f;
+  unsigned long long hint_q = 0, hint_items = 0;
+};
+Knobs g_knobs;
+std::once_flag g_knobs_once;
+
+int env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+void load_knobs() {
+  Knobs k;
+  k.mask_exclude = getenv("CCR_MASK_EXCLUDE") != nullptr;
+  k.two_cta = env_int("CCR_2CTA", -1);
+  k.split_mult = env_int("CCR_SPLIT_MULT", 0);
+  k.cap_mult = env_int("CCR_CAP_MULT", 0);
+  k.no_share = getenv("CCR_NO_SHARE") != nullptr;
+  k.no_seed = getenv("CCR_NO_SEED") != nullptr;
+  k.no_hist = getenv("CCR_NO_HIST") != nullptr;
+  { const char* v = getenv("CCR_SEED_M"); k.seed_m = v ? atoll(v) : 0; }
+  k.debug = env_int("CCR_DEBUG", 0);
+  k.debug_grid = env_int("CCR_DEBUG_GRID", 0);
+  k.keep_tau = getenv("CCR_DEBUG_KEEP_TAU") != nullptr;
+  k.throttle = env_int("CCR_THROTTLE", -1);
+  k.lead = env_int("CCR_LEAD", 0);
+  k.no_qpad = getenv("CCR_NO_QPAD") != nullptr;
+  k.prefetch = env_int("CCR_PREFETCH", -1);
+  { const char* v = getenv("CCR_DEBUG_TAU"); k.debug_tau = v ? (float)atof(v) : 0.f; }
+  { const char* v = getenv("CCR_HINT_Q"); k.hint_q = v ? strtoull(v, nullptr, 0) : 0ull; }
+  { const char* v = getenv("CCR_HINT_ITEMS"); k.hint_items = v ? strtoull(v, nullptr, 0) : 0ull; }
+  g_knobs = k;
+}
+const Knobs& knobs() {
+  std::call_once(g_knobs_once, load_knobs);
+  return g_knobs;
+}
+}  // namespace
 
 static int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -83,9 +128,10 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   int algo = flags & CCR_ALGO_MASK;
   if (algo == CCR_ALGO_AUTO) algo = ccr_choose_algo(B, n_items, D, k);
   const int sms = device_sm_count();
+  const Knobs& kn = knobs();
   pl->algo = algo;
   pl->include_mask = (algo == CCR_ALGO_TCGEN05 && nnz > 0 && h_max >= 0 && h_max <= 256 && k + h_max <= CCR_MAX_K &&
-                      !getenv("CCR_MASK_EXCLUDE")) ? 1 : 0;
+                      !kn.mask_exclude) ? 1 : 0;
   pl->k_keep = pl->include_mask ? (int)(k + h_max) : k;
   if (algo == CCR_ALGO_TCGEN05) {
     // CTA pairs (cta_group::2, 256 query rows per unit) stream each item tile once for 256 queries:
@@ -100,23 +146,20 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
       const long long tiles128 = (B + kQTile - 1) / kQTile;
       pl->two_cta = (B > kQTile && B <= 8192 && (tiles128 % 2 == 0 || tiles128 >= 17)) ? 1 : 0;
     }
-    if (const char* e2 = getenv("CCR_2CTA")) pl->two_cta = (B > kQTile && atoi(e2) != 0) ? 1 : 0;
+    if (kn.two_cta >= 0) pl->two_cta = (B > kQTile && kn.two_cta != 0) ? 1 : 0;
     const int unit_rows = kQTile * (pl->two_cta ? 2 : 1);
     pl->n_q_tiles = (int)((B + unit_rows - 1) / unit_rows);
     if (pl->n_q_tiles < 1) pl->n_q_tiles = 1;
     pl->rows_pad = pl->n_q_tiles * unit_rows;
     long long tiles = (n_items + kITile - 1) / kITile;
     pl->S = splits_tc(pl->n_q_tiles, tiles, pl->two_cta ? sms / 2 : sms);
-    if (const char* m = getenv("CCR_SPLIT_MULT")) {  // experiment knob: finer units (more waves)
-      long long s2 = (long long)pl->S * atoi(m);
+    if (kn.split_mult > 0) {  // experiment knob: finer units (more waves)
+      long long s2 = (long long)pl->S * kn.split_mult;
       if (s2 >= 1 && s2 <= tiles && s2 * 2 <= 1024) pl->S = (int)s2;
     }
     pl->halves = 2;
     pl->C = cand_capacity(pl->k_keep, 128);
-    if (const char* cm = getenv("CCR_CAP_MULT")) {  // experiment knob: larger candidate buffers, fewer prunes
-      int m = atoi(cm);
-      if (m >= 1 && m <= 16) pl->C *= m;
-    }
+    if (kn.cap_mult >= 1 && kn.cap_mult <= 16) pl->C *= kn.cap_mult;  // experiment knob: fewer prunes
     {
       // streams of one row that run in the first wave; use half of them for the bound so a few
       // late streams do not hold it back
@@ -131,7 +174,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
       const int kk = pl->k_keep;  // m * j distinct items must cover k plus every possibly-masked one
       while ((kk + j - 1) / j > use) j <<= 1;
       if (j > k) j = k;
-      pl->share_j = (s_row > 1 && !getenv("CCR_NO_SHARE")) ? j : 0;
+      pl->share_j = (s_row > 1 && !kn.no_share) ? j : 0;
       pl->share_m = (kk + j - 1) / j;
       if (pl->share_m > 256 || pl->share_m > s_row) pl->share_j = 0;
     }
@@ -154,17 +197,18 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   pl->off_counts = off; off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(int), 256);
   pl->off_ovr_hi = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u64), 256);
   pl->off_ovr_lo = off; off = align_up(off + (size_t)(nnz > 0 ? nnz : 0) * sizeof(u32), 256);
+  // [off_status, off_qpad) is zeroed by ONE memset per call: status, throttle counters, sharing state
   pl->off_status = off; off = align_up(off + sizeof(DeviceStatus), 256);
+  pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
   pl->off_gtau = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(u32), 256);
   pl->off_gq = off;     off = align_up(off + (size_t)pl->rows_pad * pl->S * pl->halves * sizeof(u32), 256);
   pl->off_hist = off;   off = align_up(off + (size_t)pl->rows_pad * kHistBins * sizeof(u32), 256);
   pl->off_hpar = off;   off = align_up(off + (size_t)pl->rows_pad * sizeof(uint2), 256);
-  pl->off_progress = off; off = align_up(off + (size_t)pl->n_q_tiles * pl->S * sizeof(int), 256);
   pl->off_qpad = off;     off = align_up(off + (size_t)kQTile * 4096 * sizeof(__nv_bfloat16), 256);
   pl->seed_m = 0; pl->seed_stride = 1; pl->seed_ld = 0; pl->off_seed = off;
-  if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !getenv("CCR_NO_SEED")) {
-    // strided sample of max(N/256, 64k) items (4096..131072, <= N/8), capped so the fp32 score matrix
-    // stays <= 512 MB
+  if (algo == CCR_ALGO_TCGEN05 && pl->share_j >= 0 && n_items >= (1 << 18) && !kn.no_seed) {
+    // strided sample of max(N/256, 64k) items (4096..131072, <= N/8); the pre-pass keeps one fp32 value
+    // per 8 sampled items (their best score), capped so that matrix stays <= 512 MB
     // With histogram sharing (no mask / include mode) the seed only has to be a sensible origin for the
     // row histograms, which take over within a few tiles: a sample of N/512 (>= 8 k) is enough and
     // measurably faster (B=4096: 43.5 -> 43.0 ms, NQ k=1001: 12.4 -> 11.8 ms).  Without it (exclude-mode
@@ -172,24 +216,30 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     // (k+h)-th best of the sample sits in its top ~1.5 %.
     const bool hist_ok = !(nnz > 0 && !pl->include_mask);
     long long m = hist_ok ? n_items / 512 : n_items / 256;
-    const long long floor_m = (hist_ok ? 8LL : 64LL) * pl->k_keep;
+    const long long floor_m = (hist_ok ? 16LL : 64LL) * pl->k_keep;  // >= 2 k_keep groups of 8
     if (m < floor_m) m = floor_m;
     if (m < 4096) m = 4096;
     if (m > 131072) m = 131072;
     if (m > n_items / 8) m = n_items / 8;
-    long long cap = (512LL << 20) / (4LL * pl->rows_pad);
+    long long cap = 8LL * (512LL << 20) / (4LL * pl->rows_pad);
     if (m > cap) m = cap;
-    if (const char* sm = getenv("CCR_SEED_M")) { long long v = atoll(sm); if (v >= 1024 && v < m) m = v; }  // experiment knob
+    if (kn.seed_m >= 1024 && kn.seed_m < m) m = kn.seed_m;  // experiment knob
     m = m / 256 * 256;
-    if (m >= 1024 && 4LL * pl->k_keep <= m) {
+    if (m >= 1024 && 16LL * pl->k_keep <= m) {
       pl->seed_m = (int)m;
       pl->seed_stride = n_items / m;
-      pl->seed_ld = m;
-      off = align_up(off + (size_t)pl->rows_pad * (size_t)m * sizeof(float), 256);
+      pl->seed_ld = m / 8;
+      off = align_up(off + (size_t)pl->rows_pad * (size_t)pl->seed_ld * sizeof(float), 256);
     }
   }
   pl->total = off;
   return true;
+}
+
+// L2 look-ahead distance (item tiles) of the tensor-core kernel; 0 = off.  See SelectParams.
+int default_prefetch_tiles(const Plan& pl, long long B) {
+  (void)pl; (void)B;
+  return 0;
 }
 
 int check_shape(long long B, long long n_items, int D, int k, int flags) {
@@ -212,7 +262,8 @@ extern "C" {
 int ccr_abi_version(void) { return CCR_ABI_VERSION; }
 const char* ccr_last_error_string(void) { return g_err; }
 
-void ccr_debug_set_status_ptr(void* device_visible_ptr) { g_status_override = device_visible_ptr; }
+void ccr_set_status_record(void* host_mapped_ptr) { g_status_record = host_mapped_ptr; }
+void ccr_debug_reload_env(void) { knobs(); load_knobs(); }
 
 void ccr_set_profile_events(void* start_event, void* stop_event) {
   g_prof_start = (cudaEvent_t)start_event;
@@ -237,16 +288,26 @@ size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k, 
   return pl.total;
 }
 
-int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* info4) {
+int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int64_t mask_max_row_nnz, int flags,
+                  int32_t* info8) {
   int rc = check_shape(B, n_items, D, k, flags | CCR_FLAG_ALLOW_SHORT);
   if (rc) return rc;
-  if (!info4) return fail(CCR_EINVAL, "info4 is null");
+  if (!info8) return fail(CCR_EINVAL, "info8 is null");
   Plan pl;
-  make_plan(B, n_items, D, k, 0, -1, flags, &pl);
-  info4[0] = pl.n_q_tiles;
-  info4[1] = pl.S;
-  info4[2] = pl.C;
-  info4[3] = pl.algo;
+  make_plan(B, n_items, D, k, mask_nnz, mask_nnz > 0 ? mask_max_row_nnz : -1, flags, &pl);
+  const bool seeded = pl.seed_m > 0 && n_items > 0 && !knobs().keep_tau;
+  int pf = pl.algo == CCR_ALGO_TCGEN05 ? default_prefetch_tiles(pl, B) : 0;
+  if (knobs().prefetch >= 0) pf = knobs().prefetch <= 64 ? knobs().prefetch : 64;
+  info8[0] = pl.n_q_tiles;
+  info8[1] = pl.S;
+  info8[2] = pl.C;
+  info8[3] = pl.algo;
+  info8[4] = pl.two_cta;
+  info8[5] = seeded ? pl.seed_m : 0;
+  // kernels one ccr_score_topk_bf16 call launches: [seeding GEMM, seed select,] fused score+select,
+  // [mask overrides,] finalize  (memsets / the short-batch query copy are not kernels of this library)
+  info8[6] = (B > 0) ? (seeded ? 2 : 0) + (n_items > 0 ? 1 : 0) + (mask_nnz > 0 ? 1 : 0) + 1 : 0;
+  info8[7] = pf;
   return CCR_OK;
 }
 
@@ -267,6 +328,10 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     return fail(CCR_EINVAL, "bad mask_mode %d", mask_mode);
   const bool has_mask = mask_mode != CCR_MASK_NONE && mask_indptr != nullptr;
   if (has_mask && (!mask_cols || !mask_vals)) return fail(CCR_EINVAL, "mask_cols / mask_vals null");
+  if (flags & CCR_FLAG_PACKED_KEYS) {
+    if (mask_mode == CCR_MASK_ADD) return fail(CCR_EINVAL, "CCR_FLAG_PACKED_KEYS: float64 priors do not fit a float32 key");
+    if (id_offset < 0 || id_offset + n_items > (1LL << 32)) return fail(CCR_EUNSUPPORTED, "CCR_FLAG_PACKED_KEYS: global ids must be < 2^32");
+  }
   cudaStream_t st = (cudaStream_t)stream;
 
   const long long nnz = has_mask ? mask_nnz : 0;
@@ -276,72 +341,71 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   if (!workspace || workspace_bytes < pl.total)
     return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, pl.total);
   unsigned char* ws = (unsigned char*)workspace;
-  DeviceStatus* status = g_status_override ? (DeviceStatus*)g_status_override : (DeviceStatus*)(ws + pl.off_status);
-  cudaError_t e = cudaSuccess;
-  if (!g_status_override) e = cudaMemsetAsync(status, 0, sizeof(DeviceStatus), st);
-  if (e != cudaSuccess) return fail(CCR_ECUDA, "memset status: %s", cudaGetErrorString(e));
+  const Knobs& kn = knobs();
+  // watchdog record: the caller's host-mapped one (readable after a device trap) or a workspace slot
+  DeviceStatus* status = g_status_record ? (DeviceStatus*)g_status_record : (DeviceStatus*)(ws + pl.off_status);
+  // one memset for everything that must start from zero: status slot, throttle counters and (unless
+  // the debug knob keeps them) thresholds, published quantiles, histograms and their parameters
+  cudaError_t e = cudaMemsetAsync(ws + pl.off_status, 0, (kn.keep_tau ? pl.off_gtau : pl.off_qpad) - pl.off_status, st);
+  if (e != cudaSuccess) return fail(CCR_ECUDA, "memset call state: %s", cudaGetErrorString(e));
 
-  SelectParams sp;
+  SelectParams sp = {};
   sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B; sp.q_rows = (int)B;
   sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
-  sp.k = k; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles; sp.two_cta = pl.two_cta;
+  sp.k = k; sp.k_keep = pl.k_keep; sp.C = pl.C; sp.S = pl.S; sp.n_q_tiles = pl.n_q_tiles; sp.two_cta = pl.two_cta;
   sp.mask_indptr = has_mask ? (const long long*)mask_indptr : nullptr;
   sp.mask_cols = (has_mask && !pl.include_mask) ? mask_cols : nullptr;
   sp.cand = (u64*)(ws + pl.off_cand);
   sp.counts = (int*)(ws + pl.off_counts);
   sp.status = status;
-  { const char* d = getenv("CCR_DEBUG"); sp.debug = d ? atoi(d) : 0; }
-  { const char* d = getenv("CCR_DEBUG_TAU"); sp.debug_tau = d ? (float)atof(d) : 0.f; }
+  sp.debug = kn.debug; sp.debug_tau = kn.debug_tau; sp.debug_grid = kn.debug_grid;
+  sp.hint_q = kn.hint_q; sp.hint_items = kn.hint_items;
   sp.g_tau = nullptr; sp.g_q = nullptr; sp.S_row = pl.S * pl.halves; sp.share_j = pl.share_j; sp.share_m = pl.share_m;
-  sp.dense_out = nullptr; sp.ld_out = 0;
+  sp.dense_out = nullptr; sp.ld_out = 0; sp.store_max8 = 0;
   sp.progress = nullptr;
+  sp.prefetch_tiles = (pl.algo == CCR_ALGO_TCGEN05) ? default_prefetch_tiles(pl, B) : 0;
+  if (kn.prefetch >= 0) sp.prefetch_tiles = kn.prefetch <= 64 ? kn.prefetch : 64;
   sp.g_hist = nullptr; sp.g_hpar = nullptr;
   // bounded drift between the units that stream the same item split: default for CTA pairs (their
   // deeper pipeline lets a leader run away from its followers: 99 GB instead of 15 GB of DRAM reads
   // at B=4096), opt-in for single CTAs where it was measured to cost more than it saves
   bool use_throttle = pl.two_cta && pl.n_q_tiles > 1;
-  if (const char* t = getenv("CCR_THROTTLE")) use_throttle = atoi(t) != 0;
+  if (kn.throttle >= 0) use_throttle = kn.throttle != 0;
   sp.lead_tiles = 16;
-  if (const char* t = getenv("CCR_LEAD")) { int v = atoi(t); if (v >= 1 && v <= 4096) sp.lead_tiles = v; }
-  if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) {
-    sp.progress = (int*)(ws + pl.off_progress);
-    e = cudaMemsetAsync(sp.progress, 0, (size_t)pl.n_q_tiles * pl.S * sizeof(int), st);
-    if (e != cudaSuccess) return fail(CCR_ECUDA, "memset progress: %s", cudaGetErrorString(e));
-  }
+  if (kn.lead >= 1 && kn.lead <= 4096) sp.lead_tiles = kn.lead;
+  if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) sp.progress = (int*)(ws + pl.off_progress);
   if (pl.share_j > 0 || pl.seed_m > 0) {
     sp.g_tau = (u32*)(ws + pl.off_gtau);
     sp.g_q = (u32*)(ws + pl.off_gq);
-    e = (getenv("CCR_DEBUG_KEEP_TAU") != nullptr) ? cudaSuccess : cudaMemsetAsync(ws + pl.off_gtau, 0, pl.off_seed - pl.off_gtau, st);
-    if (e != cudaSuccess) return fail(CCR_ECUDA, "memset share state: %s", cudaGetErrorString(e));
   }
-  if (pl.seed_m > 0 && n_items > 0 && !getenv("CCR_DEBUG_KEEP_TAU")) {
+  if (pl.seed_m > 0 && n_items > 0 && !kn.keep_tau) {
     // threshold seeding pre-pass: scores of a strided item sample -> per-row lower bound in g_tau
     SelectParams ss = sp;
     ss.n_items = pl.seed_m; ss.ldi = ldi * pl.seed_stride;
     ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
-    ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld;
-    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr;
+    ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld; ss.store_max8 = 1;
+    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr; ss.prefetch_tiles = 0;
     // the histogram needs the seed bound as its origin and counts every streamed item, so it is
     // off in exclude-mask mode (masked items must not be counted)
-    const bool use_hist = sp.mask_cols == nullptr && !getenv("CCR_NO_HIST");
+    const bool use_hist = sp.mask_cols == nullptr && !kn.no_hist;
     if (use_hist) { sp.g_hist = (u32*)(ws + pl.off_hist); sp.g_hpar = (const uint2*)(ws + pl.off_hpar); }
     ss.two_cta = 0; ss.n_q_tiles = pl.rows_pad / kQTile;
     long long tiles = (pl.seed_m + kITile - 1) / kITile;
     ss.S = splits_tc(ss.n_q_tiles, tiles, device_sm_count());
     int lr0 = launch_select_tc(ss, st, device_sm_count());
     if (lr0) return fail(CCR_ECUDA, "seed GEMM launch failed (%d)", lr0);
-    lr0 = launch_seed_tau(ss.dense_out, pl.seed_ld, pl.seed_m, (int)B, k, has_mask ? (const long long*)mask_indptr : nullptr,
+    // per row: the (k + h)-th largest of the seed_m / 8 group maxima
+    lr0 = launch_seed_tau(ss.dense_out, pl.seed_ld, (int)pl.seed_ld, (int)B, k, has_mask ? (const long long*)mask_indptr : nullptr,
                           sp.g_tau, use_hist ? (uint2*)(ws + pl.off_hpar) : nullptr, st);
     if (lr0) return fail(CCR_ECUDA, "seed select launch failed: %s", cudaGetErrorString((cudaError_t)lr0));
   }
 
-  if (pl.algo == CCR_ALGO_TCGEN05 && B < kQTile && n_items > 0 && !getenv("CCR_NO_QPAD")) {
-    // short batch: stage the queries in a zero-padded [128, D] block so that no TMA box of the
-    // query operand is out of bounds (measurably faster than hardware zero-fill of 120+ rows)
+  if (pl.algo == CCR_ALGO_TCGEN05 && B < kQTile && n_items > 0 && !kn.no_qpad) {
+    // short batch: stage the queries in a [128, D] block so that no TMA box of the query operand is
+    // out of bounds (measurably faster than hardware zero-fill of 120+ rows).  Rows >= B of the block
+    // keep whatever the workspace held: MMA rows are independent and padding rows never select.
     __nv_bfloat16* qp = (__nv_bfloat16*)(ws + pl.off_qpad);
-    e = cudaMemsetAsync(qp, 0, (size_t)kQTile * D * sizeof(__nv_bfloat16), st);
-    if (e == cudaSuccess)
-      e = cudaMemcpy2DAsync(qp, (size_t)D * 2, q, (size_t)ldq * 2, (size_t)D * 2, (size_t)B, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemcpy2DAsync(qp, (size_t)D * 2, q, (size_t)ldq * 2, (size_t)D * 2, (size_t)B, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail(CCR_ECUDA, "query padding: %s", cudaGetErrorString(e));
     sp.q = qp; sp.ldq = D; sp.q_rows = kQTile;
   }
@@ -359,7 +423,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
 
   if (has_mask && nnz > 0) {
     OverrideParams op;
-    op.q = sp.q; op.ldq = ldq; op.B = (int)B; op.items = sp.items; op.ldi = ldi; op.n_items = n_items; op.D = D;
+    op.q = sp.q; op.ldq = sp.ldq; op.B = (int)B;  // sp.q may be the padded staging block (pitch D) op.items = sp.items; op.ldi = ldi; op.n_items = n_items; op.D = D;
     op.mask_indptr = sp.mask_indptr; op.mask_cols = mask_cols; op.mask_vals = mask_vals; op.nnz = nnz;
     op.mode = mask_mode; op.ovr_hi = (u64*)(ws + pl.off_ovr_hi); op.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
     lr = launch_overrides(op, st);
@@ -373,6 +437,8 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   fp.mask_indptr = (has_mask && nnz > 0) ? sp.mask_indptr : nullptr;
   fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
   fp.id_offset = id_offset; fp.out_scores = out_scores; fp.out_scores64 = out_scores64;
+  fp.out_keys = nullptr;
+  if (flags & CCR_FLAG_PACKED_KEYS) { fp.out_keys = (u64*)out_scores64; fp.out_scores64 = nullptr; }
   fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
   if (lr) return fail(CCR_ECUDA, "finalize kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
@@ -387,6 +453,27 @@ int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B,
   int lr = launch_merge_topk(scores64, (const long long*)ids, G, B, k_in, k_out, out_scores, out_scores64,
                              (long long*)out_ids, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "merge kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_merge_topk_keys(const uint64_t* keys, int G, int64_t B, int k_in, int k_out, float* out_scores,
+                        int64_t* out_ids, void* stream) {
+  if (G < 1 || B < 0 || k_in < 1 || k_out < 1) return fail(CCR_EINVAL, "bad merge shape G=%d B=%lld k_in=%d k_out=%d", G, (long long)B, k_in, k_out);
+  if (B == 0) return CCR_OK;
+  if (!keys || !out_ids) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_merge_keys((const u64*)keys, G, B, k_in, k_out, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+  if (lr == (int)cudaErrorInvalidValue) return fail(CCR_EUNSUPPORTED, "merge: G * k_in = %lld keys do not fit shared memory", (long long)G * k_in);
+  if (lr) return fail(CCR_ECUDA, "key merge kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_mask_column_shard(const int64_t* indptr, const int32_t* cols, const double* vals, int64_t B, int64_t col_lo,
+                          int64_t col_hi, int64_t* out_indptr, int32_t* out_cols, double* out_vals, void* stream) {
+  if (B < 0 || col_lo < 0 || col_hi < col_lo || col_hi > (1LL << 31) - 1) return fail(CCR_EINVAL, "bad mask shard range");
+  if (!indptr || !out_indptr) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_mask_shard((const long long*)indptr, cols, vals, B, (int)col_lo, (int)col_hi, (long long*)out_indptr,
+                             out_cols, out_vals, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "mask shard kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
 }
 
@@ -477,7 +564,7 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
   unsigned char* ws = (unsigned char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   const long long* indptr = has_mask ? (const long long*)mask_indptr : nullptr;
-  int lr = launch_select_dense(scores, ld, B, n_cols, k, indptr, pl.C, pl.S, (u64*)ws, (int*)(ws + pl.off_counts), st);
+  int lr = launch_select_dense(scores, ld, B, n_cols, k, (int)(k + h), indptr, pl.C, pl.S, (u64*)ws, (int*)(ws + pl.off_counts), st);
   if (lr) return fail(CCR_ECUDA, "dense select launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   if (has_mask) {
     lr = launch_override_dense(scores, ld, (int)B, n_cols, indptr, mask_cols, mask_vals, nnz, mask_mode,
@@ -490,7 +577,7 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
   fp.drop_cols = has_mask ? mask_cols : nullptr;
   fp.mask_indptr = indptr;
   fp.ovr_hi = (u64*)(ws + pl.off_ovr_hi); fp.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
-  fp.id_offset = 0; fp.out_scores = out_scores; fp.out_scores64 = out_scores64; fp.out_ids = (long long*)out_ids;
+  fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = out_scores64; fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
   if (lr) return fail(CCR_ECUDA, "finalize launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
@@ -565,7 +652,7 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
   FinalizeParams fp;
   fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
   fp.g_tau = nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
-  fp.id_offset = 0; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
+  fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
   if (lr) return fail(CCR_ECUDA, "finalize launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;

@@ -151,7 +151,7 @@ int launch_select_simt(const SelectParams& p, cudaStream_t st) {
 __global__ void __launch_bounds__(256) override_kernel(OverrideParams p) {
   const int lane = threadIdx.x & 31;
   const long long e = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (e >= p.nnz) return;
+  if (e >= p.nnz || e >= p.mask_indptr[p.B]) return;  // nnz may be an upper bound of indptr[B]
   // row of entry e: largest r with indptr[r] <= e
   int lo = 0, hi = p.B;  // invariant: indptr[lo] <= e < indptr[hi]
   while (hi - lo > 1) {
@@ -422,12 +422,15 @@ __global__ void __launch_bounds__(kFinMaxThreads) finalize_kernel(FinalizeParams
     long long o = (long long)row * k + i;
     if (i < nwin) {
       double v = unord64(w_hi[i]);
+      const long long gid = (long long)(0xFFFFFFFFu - w_lo[i]) + p.id_offset;
       if (p.out_scores) p.out_scores[o] = (float)v;
-      if (p.out_scores64) p.out_scores64[o] = v;
-      p.out_ids[o] = (long long)(0xFFFFFFFFu - w_lo[i]) + p.id_offset;
+      if (p.out_keys) p.out_keys[o] = make_key((float)v, (u32)gid);  // exchange format: [ord32 : ~global id]
+      else if (p.out_scores64) p.out_scores64[o] = v;
+      p.out_ids[o] = gid;
     } else {
       if (p.out_scores) p.out_scores[o] = -INFINITY;
-      if (p.out_scores64) p.out_scores64[o] = -INFINITY;
+      if (p.out_keys) p.out_keys[o] = 0ull;  // padding: below every real key
+      else if (p.out_scores64) p.out_scores64[o] = -INFINITY;
       p.out_ids[o] = -1;
     }
   }
@@ -531,6 +534,162 @@ int launch_merge_topk(const double* s, const long long* ids, int G, long long B,
   } else {
     merge_topk_kernel<false><<<(unsigned)B, 256, 0, st>>>(s, ids, G, B, k_in, k_out, os, os64, oi);
   }
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// G-way merge of packed 64-bit keys ([ord32(score) : ~global id], larger = better, 0 = padding):
+// the 8-byte-per-entry exchange format of the row-sharded path when the order is decided in
+// float32.  One block per query row; the G sorted runs are staged in shared memory and merged
+// pairwise, log2(G) rounds of merge-path merges: every thread finds the start of its output
+// segment with one co-rank binary search (~log2 k probes) and then merges kMergeSeg keys
+// sequentially.  Runs are truncated to k_out after every round, so the rounds produce
+// (G/2 + G/4 + ... + 1) * k_out keys in total -- against ~G log2(k) probes for EVERY entry in the
+// rank-by-search kernel above.
+// =======================================================================================
+constexpr int kMergeSeg = 4;
+
+__global__ void __launch_bounds__(1024) merge_keys_kernel(const u64* __restrict__ keys, int G, long long B, int k_in,
+                                                          int k_out, int n0, float* os, long long* oi) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* buf0 = reinterpret_cast<u64*>(merge_smem);   // n0 keys: the G input runs, later the even rounds' outputs
+  u64* buf1 = buf0 + n0;                            // the odd rounds' outputs
+  const long long row = blockIdx.x;
+  for (int e = threadIdx.x; e < G * k_in; e += blockDim.x) {
+    const int g = e / k_in, i = e - g * k_in;
+    buf0[e] = keys[((long long)g * B + row) * k_in + i];
+  }
+  __syncthreads();
+  u64* src = buf0;
+  u64* dst = buf1;
+  int runs = G, len = k_in;
+  while (runs > 1) {
+    const int pairs = runs >> 1, odd = runs & 1;
+    const int out_len = 2 * len < k_out ? 2 * len : k_out;
+    const int segs = (out_len + kMergeSeg - 1) / kMergeSeg;
+    for (int w = threadIdx.x; w < pairs * segs; w += blockDim.x) {
+      const int pr = w / segs, sg = w - pr * segs;
+      const u64* a = src + (size_t)(2 * pr) * len;
+      const u64* b = a + len;
+      const int d = sg * kMergeSeg;  // diagonal: outputs [d, d + kMergeSeg)
+      // co-rank: i keys of a and d - i keys of b precede output d (keys are distinct except padding
+      // zeros, whose relative order does not matter)
+      int lo = d > len ? d - len : 0, hi = d < len ? d : len;
+      while (lo < hi) {
+        const int i = (lo + hi) >> 1;
+        if (a[i] > b[d - i - 1]) lo = i + 1; else hi = i;
+      }
+      int i = lo, j = d - lo;
+      u64* o = dst + (size_t)pr * out_len + d;
+      const int n = out_len - d < kMergeSeg ? out_len - d : kMergeSeg;
+      for (int t = 0; t < n; ++t) {
+        const bool take_a = (j >= len) || (i < len && a[i] > b[j]);
+        o[t] = take_a ? a[i++] : b[j++];
+      }
+    }
+    if (odd) {  // the unpaired run moves on unchanged (truncated)
+      const u64* a = src + (size_t)(2 * pairs) * len;
+      const int n = len < out_len ? len : out_len;
+      for (int t = threadIdx.x; t < out_len; t += blockDim.x) dst[(size_t)pairs * out_len + t] = t < n ? a[t] : 0ull;
+    }
+    __syncthreads();
+    u64* tmp = src; src = dst; dst = tmp;
+    runs = pairs + odd;
+    len = out_len;
+  }
+  for (int r = threadIdx.x; r < k_out; r += blockDim.x) {
+    const u64 key = r < len ? src[r] : 0ull;
+    const long long o = row * k_out + r;
+    if (key) { if (os) os[o] = key_score(key); oi[o] = (long long)key_id(key); }
+    else { if (os) os[o] = -INFINITY; oi[o] = -1; }
+  }
+}
+
+int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi,
+                      cudaStream_t st) {
+  if (B == 0) return 0;
+  const int ol = 2 * k_in < k_out ? 2 * k_in : k_out;
+  // ping-pong buffers sized by replaying the rounds: round r reads buf[(r-1)&1], writes buf[r&1]
+  size_t need[2] = {(size_t)G * k_in, 0};
+  {
+    int runs = G, len = k_in, r = 1;
+    while (runs > 1) {
+      const int out_len = 2 * len < k_out ? 2 * len : k_out;
+      runs = (runs >> 1) + (runs & 1);
+      const size_t n = (size_t)runs * out_len;
+      if (n > need[r & 1]) need[r & 1] = n;
+      len = out_len;
+      ++r;
+    }
+  }
+  const size_t n0 = need[0], n1 = need[1];
+  const size_t smem = (n0 + n1) * sizeof(u64);
+  if (smem > 220 * 1024) return (int)cudaErrorInvalidValue;
+  static bool attr_done[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = -1; }
+  if (dev < 0 || !attr_done[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0) attr_done[dev] = true;
+  }
+  int threads = (int)(((size_t)(G / 2) * ((ol + kMergeSeg - 1) / kMergeSeg) + 31) / 32 * 32);
+  if (threads < 128) threads = 128;
+  if (threads > 1024) threads = 1024;
+  merge_keys_kernel<<<(unsigned)B, threads, smem, st>>>(keys, G, B, k_in, k_out, (int)n0, os, oi);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
+// Column shard of a mask CSR on the device (row-sharded tables): keep the entries with
+// lo <= col < hi, re-based to local columns.  Columns are sorted inside a row, so the kept entries
+// of a row are one contiguous range found by two binary searches; one block scans the row counts
+// (B is a query batch: a few thousand rows) and copies the ranges.
+// =======================================================================================
+__global__ void __launch_bounds__(1024) mask_shard_kernel(const long long* __restrict__ indptr,
+                                                          const int* __restrict__ cols,
+                                                          const double* __restrict__ vals, long long B, int lo, int hi,
+                                                          long long* __restrict__ out_indptr, int* __restrict__ out_cols,
+                                                          double* __restrict__ out_vals) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { s_carry = 0; out_indptr[0] = 0; }
+  __syncthreads();
+  for (long long r0 = 0; r0 < B; r0 += blockDim.x) {
+    const long long r = r0 + tid;
+    long long a = 0, b = 0;
+    if (r < B) {
+      const long long beg = indptr[r], end = indptr[r + 1];
+      long long x = beg, y = end;
+      while (x < y) { const long long m = (x + y) >> 1; if (cols[m] < lo) x = m + 1; else y = m; }
+      a = x; y = end;
+      while (x < y) { const long long m = (x + y) >> 1; if (cols[m] < hi) x = m + 1; else y = m; }
+      b = x;
+    }
+    const long long cnt = b - a;
+    long long incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const long long v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    long long base = s_carry;
+    for (int w = 0; w < warp; ++w) base += s_warp[w];
+    const long long start = base + incl - cnt;
+    if (r < B) {
+      out_indptr[r + 1] = start + cnt;
+      for (long long e = 0; e < cnt; ++e) { out_cols[start + e] = cols[a + e] - lo; out_vals[start + e] = vals[a + e]; }
+    }
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = base + incl;
+    __syncthreads();
+  }
+}
+
+int launch_mask_shard(const long long* indptr, const int* cols, const double* vals, long long B, int lo, int hi,
+                      long long* out_indptr, int* out_cols, double* out_vals, cudaStream_t st) {
+  if (B < 0) return (int)cudaErrorInvalidValue;
+  mask_shard_kernel<<<1, 1024, 0, st>>>(indptr, cols, vals, B, lo, hi, out_indptr, out_cols, out_vals);
   return (int)cudaGetLastError();
 }
 
@@ -818,7 +977,7 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
 constexpr int kDenseThreads = 256;
 
 __global__ void __launch_bounds__(kDenseThreads) select_dense_kernel(const float* __restrict__ scores, long long ld,
-                                                                     long long N, int k,
+                                                                     long long N, int k, int k_keep,
                                                                      const long long* __restrict__ mask_indptr, int C,
                                                                      int S, u64* cand, int* counts) {
   __shared__ int s_cnt;
@@ -827,7 +986,9 @@ __global__ void __launch_bounds__(kDenseThreads) select_dense_kernel(const float
   __shared__ u32 s_hist[256];
   const int tid = threadIdx.x, split = blockIdx.x;
   const long long row = blockIdx.y;
-  const int k_row = k + (mask_indptr ? (int)(mask_indptr[row + 1] - mask_indptr[row]) : 0);
+  // buffers are sized for k_keep = k + mask_max_row_nnz: never trust the CSR beyond that
+  const long long k_csr = (long long)k + (mask_indptr ? (mask_indptr[row + 1] - mask_indptr[row]) : 0);
+  const int k_row = k_csr < (long long)k_keep ? (int)k_csr : k_keep;
   long long per = (N + S - 1) / S;
   per = (per + kDenseSlack - 1) / kDenseSlack * kDenseSlack;
   const long long i0 = (long long)split * per;
@@ -878,11 +1039,11 @@ __global__ void __launch_bounds__(256) override_dense_kernel(const float* __rest
   ovr_lo[e] = 0xFFFFFFFFu - (u32)col;
 }
 
-int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k,
+int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k, int k_keep,
                         const long long* mask_indptr, int C, int S, u64* cand, int* counts, cudaStream_t st) {
   if (B <= 0) return 0;
   dim3 grid((unsigned)S, (unsigned)B);
-  select_dense_kernel<<<grid, kDenseThreads, 0, st>>>(scores, ld, N, k, mask_indptr, C, S, cand, counts);
+  select_dense_kernel<<<grid, kDenseThreads, 0, st>>>(scores, ld, N, k, k_keep, mask_indptr, C, S, cand, counts);
   return (int)cudaGetLastError();
 }
 

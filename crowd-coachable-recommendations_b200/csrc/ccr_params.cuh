@@ -17,6 +17,10 @@ struct SelectParams {
   long long n_items;
   int D;
   int k;
+  int k_keep;     // upper bound of the candidates one row must keep (k + mask_max_row_nnz in include
+                  // mode, else k): the candidate buffers are sized for it, so per-row counts derived from
+                  // the CSR are clamped to it (a caller that under-reports mask_max_row_nnz must not be
+                  // able to overrun a buffer)
   int C;          // candidate capacity per (row, split)
   int S;          // item splits
   int n_q_tiles;  // query tiles (tensor-core kernel: 128 rows, or 256 when two_cta) or groups of 8 (SIMT)
@@ -50,11 +54,24 @@ struct SelectParams {
   // tiles L2-resident so the table is read from HBM once): tiles issued so far, per unit
   int* progress;  // [n_units], zeroed per call; null = off
   int lead_tiles; // max lead (item tiles) of a producer over the slowest unit on the same split
-  // store mode (threshold seeding pre-pass): write fp32 scores instead of selecting
+  // L2 look-ahead: the units that stream one item split take turns issuing
+  // cp.async.bulk.prefetch.tensor for the tile `prefetch_tiles` ahead of their own position (each
+  // tile is requested once per split, by one unit), so the demand loads of every unit hit L2 and the
+  // bytes in flight towards HBM are no longer limited by the shared-memory ring.  0 = off.
+  int prefetch_tiles;
+  // L2 eviction-priority hints of the two operand streams (createpolicy-style 64-bit descriptors,
+  // 0 = none): diagnostics knob, see CCR_HINT_Q / CCR_HINT_ITEMS
+  u64 hint_q, hint_items;
+  // store mode: write fp32 scores instead of selecting (dense score tiles for as_tensor / _argsort).
+  // With store_max8 (threshold seeding pre-pass) only the best score of every 8 consecutive items is
+  // written: the k-th largest of those group maxima is a lower bound of the k-th largest item score,
+  // carried by k distinct items -- 1/8 of the bytes, and the selection pass over them is 8x shorter.
   float* dense_out;      // [rows_pad][ld_out], null in select mode
-  long long ld_out;
+  long long ld_out;      // floats per row: >= n_items rounded up to 256 (full) or / 8 (store_max8)
+  int store_max8;
   float debug_tau;  // CCR_DEBUG & 16: fixed threshold, no prune (cnt wraps); & 32: also no store
   int debug;  // CCR_DEBUG bits (env, diagnostics only): 1 = skip selection, keep pipeline
+  int debug_grid;  // CCR_DEBUG_GRID: cap on the persistent grid (0 = none)
 };
 
 struct FinalizeParams {
@@ -74,6 +91,7 @@ struct FinalizeParams {
   long long id_offset;
   float* out_scores;
   double* out_scores64;
+  u64* out_keys;   // CCR_FLAG_PACKED_KEYS: [ord32(float32 score) : ~uint32 global id] instead of out_scores64
   long long* out_ids;
 };
 
@@ -104,6 +122,10 @@ int launch_overrides(const OverrideParams& p, cudaStream_t st);
 int launch_finalize(const FinalizeParams& p, cudaStream_t st);
 int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,
                       float* os, double* os64, long long* oi, cudaStream_t st);
+int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi,
+                      cudaStream_t st);
+int launch_mask_shard(const long long* indptr, const int* cols, const double* vals, long long B, int lo, int hi,
+                      long long* out_indptr, int* out_cols, double* out_vals, cudaStream_t st);
 int launch_ingest_f32(const float* src, long long n, int D, long long ld_src, __nv_bfloat16* dst,
                       long long ld_dst, int normalize, cudaStream_t st);
 int launch_normalize_bf16(const __nv_bfloat16* src, long long n, int D, long long ld_src,
@@ -113,7 +135,7 @@ int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const _
 
 // dense top-k (ccr_kernels.cu)
 constexpr int kDenseSlack = 1024;  // columns one block scans between two prune checks
-int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k,
+int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k, int k_keep,
                         const long long* mask_indptr, int C, int S, u64* cand, int* counts, cudaStream_t st);
 int launch_override_dense(const float* scores, long long ld, int B, long long N, const long long* mask_indptr,
                           const int* mask_cols, const double* mask_vals, long long nnz, int mode, u64* ovr_hi,

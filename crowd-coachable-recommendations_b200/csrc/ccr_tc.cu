@@ -103,10 +103,19 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity, DeviceStatus* st
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, u64* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, u64* bar, u64 hint) {
+  if (hint)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// L2 look-ahead of one box of the tensor map (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 // ---- cta_group::2 (CTA pair) variants ----
 __device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -121,10 +130,15 @@ __device__ __forceinline__ u32 mapa_u32(const void* p, u32 rank) {
   return r;
 }
 // TMA load into OWN shared memory whose bytes are accounted on the LEADER CTA's mbarrier
-__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, int c0, int c1, u32 leader_bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, int c0, int c1, u32 leader_bar, u64 hint) {
+  if (hint)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_commit_2cta(u64* bar) {  // arrives on `bar`'s offset in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -483,7 +497,16 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // should one not be running (shared GPU), the wait gives up after 2 ms and throttling is
         // dropped for the rest of the unit.
         bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
+        const int n_peers = peer_hi - peer_lo, my_peer = unit - peer_lo;
         for (long long t = t0; t < t1; ++t) {
+          if (p.prefetch_tiles > 0) {
+            // L2 look-ahead, one requester per tile and split: the peers take turns
+            const long long tp = t + p.prefetch_tiles;
+            if (tp < t1 && (int)((tp - t0) % n_peers) == my_peer) {
+              for (int kb = 0; kb < num_kb; ++kb)
+                tma_prefetch_2d(&tmap_items, kb * kKBlock, (int)(tp * kITile) + crank * G::kItemRows);
+            }
+          }
           if (throttle && ((t - t0) & 7) == 0) {
             const int mine = (int)(t - t0);
             asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(mine) : "memory");
@@ -510,12 +533,12 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
               if (crank == 0) mbar_expect_tx(&sh->full[stage], 2 * kStageBytes);
               const u32 lbar = mapa_u32(&sh->full[stage], 0);
-              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar);
-              tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar);
+              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar, p.hint_q);
+              tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar, p.hint_items);
             } else {
               mbar_expect_tx(&sh->full[stage], kStageBytes);
-              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
-              tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage]);
+              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage], p.hint_q);
+              tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage], p.hint_items);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -564,15 +587,19 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   } else {
    // ---- selection warpgroups: take the registers the feeders released ----
    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kSelRegs));
-   if (kMode == 2) {
-    // ===== store epilogue: thread == query row, writes its 128 columns of the tile as fp32 =====
+   if (kMode >= 2) {
+    // ===== store epilogue: thread == query row; writes its 128 columns of the tile as fp32 (kMode 2)
+    //       or the best score of every 8 columns (kMode 3, threshold seeding) =====
     const int quad = warp & 3, half = warp >> 2;
     const int row_in_tile = quad * 32 + lane;
     int acc = 0; u32 acc_phase = 0;
+    const bool vec_ok = (p.ld_out & 3) == 0 && ((uintptr_t)p.dense_out & 15) == 0;
     for (int unit = cid; unit < n_units; unit += n_cl) {
       const int qt = unit % p.n_q_tiles, u = unit / p.n_q_tiles;
       const long long t0 = (long long)u * tiles_total / p.S, t1 = (long long)(u + 1) * tiles_total / p.S;
-      float* orow = p.dense_out + (long long)(qt * kQRows + crank * kQTile + row_in_tile) * p.ld_out;
+      const int row = qt * kQRows + crank * kQTile + row_in_tile;
+      const bool valid_row = row < p.B;
+      float* orow = p.dense_out + (long long)row * p.ld_out;
       for (long long t = t0; t < t1; ++t) {
         mbar_wait(&sh->tmem_full[acc], acc_phase, p.status, 400 + acc);
         tc_fence_after();
@@ -583,11 +610,29 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           u32 v[32];
           tmem_ld_32x32b_x32(taddr0 + (u32)(32 * c), v);
           tmem_ld_wait();
-          float4* o4 = reinterpret_cast<float4*>(orow + col0 + 32 * c);  // ld_out % 256 == 0: in bounds
+          const long long cc = col0 + 32 * c;
+          if (kMode == 3) {
+            // sampled items beyond n_items are zero rows (TMA fill): a 0 score may only raise a group
+            // maximum that is negative, so such groups are written as -inf instead
+            if (valid_row) {
+              float m8[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              for (int g = 0; g < 4; ++g) m8[g] = (cc + 8 * g + 8 <= p.n_items) ? max8(v, g) : -INFINITY;
+              *reinterpret_cast<float4*>(orow + (cc >> 3)) = make_float4(m8[0], m8[1], m8[2], m8[3]);
+            }
+          } else if (valid_row) {
+            if (vec_ok && cc + 32 <= p.n_items) {
+              float4* o4 = reinterpret_cast<float4*>(orow + cc);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cc + j < p.n_items) orow[cc + j] = __uint_as_float(v[j]);
+            }
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -632,7 +677,10 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (hp.y) { st.hist = p.g_hist + (long long)row * kHistBins; st.hbase = hp.x; st.hshift = hp.y - 1u; }
       }
       st.k_row = k;
-      if (!kMask && p.mask_indptr && valid_row) st.k_row = k + (int)(p.mask_indptr[row + 1] - p.mask_indptr[row]);
+      if (!kMask && p.mask_indptr && valid_row) {
+        const long long kr = (long long)k + (p.mask_indptr[row + 1] - p.mask_indptr[row]);
+        st.k_row = kr < (long long)p.k_keep ? (int)kr : p.k_keep;  // buffers are sized for k_keep
+      }
       if (kMask && valid_row) {
         st.mbeg = p.mask_indptr[row]; st.mend = p.mask_indptr[row + 1];
         for (long long e = st.mbeg; e < st.mend; ++e) {
@@ -848,12 +896,22 @@ template <int kMode, int kCta>
 static int launch_variant(const CUtensorMap& tq, const CUtensorMap& ti, const SelectParams& p, cudaStream_t st,
                           int num_sms) {
   auto kern = select_tc_kernel<kMode, kCta>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
-  if (e != cudaSuccess) return (int)e;
+  cudaError_t e = cudaSuccess;
+  {
+    // the attribute is per function and device: set it once, not on every launch
+    static bool attr_done[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = -1; }
+    if (dev < 0 || !attr_done[dev]) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0) attr_done[dev] = true;
+    }
+  }
   const int n_units = p.n_q_tiles * p.S;
   int workers = num_sms / kCta;  // persistent CTAs (kCta = 1) or CTA pairs (kCta = 2)
   if (n_units < workers) workers = n_units;
-  if (const char* g = getenv("CCR_DEBUG_GRID")) { int v = atoi(g) / kCta; if (v > 0 && v < workers) workers = v; }
+  if (p.debug_grid > 0 && p.debug_grid / kCta < workers) workers = p.debug_grid / kCta;
   if (workers < 1) workers = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(workers * kCta));
@@ -875,7 +933,7 @@ int launch_select_tc(const SelectParams& p, cudaStream_t st, int num_sms) {
   if (r) return r;
   r = make_tmap(&ti, p.items, p.n_items, p.D, p.ldi, p.two_cta ? kITile / 2 : kITile);
   if (r) return r;
-  if (p.dense_out) return launch_variant<2, 1>(tq, ti, p, st, num_sms);
+  if (p.dense_out) return p.store_max8 ? launch_variant<3, 1>(tq, ti, p, st, num_sms) : launch_variant<2, 1>(tq, ti, p, st, num_sms);
   if (p.two_cta) return p.mask_cols ? launch_variant<1, 2>(tq, ti, p, st, num_sms) : launch_variant<0, 2>(tq, ti, p, st, num_sms);
   return p.mask_cols ? launch_variant<1, 1>(tq, ti, p, st, num_sms) : launch_variant<0, 1>(tq, ti, p, st, num_sms);
 }

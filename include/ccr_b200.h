@@ -15,8 +15,11 @@
  *     default stream);
  *   - return value: 0 on success, negative CCR_E* on failure; ccr_last_error_string()
  *     returns a thread-local description of the last failure;
- *   - re-entrant and stream-ordered; no global mutable state besides a per-device cache of
- *     immutable device attributes.
+ *   - re-entrant and stream-ordered.  Process-wide state is limited to: a per-device cache of
+ *     immutable device attributes; the diagnostic CCR_* environment knobs, parsed once on first
+ *     use (ccr_debug_reload_env re-reads them); the optional watchdog record pointer
+ *     (ccr_set_status_record).  The measurement hook (ccr_set_profile_events) is per host thread.
+ *     Calls that share a workspace must be ordered on one stream.
  */
 #ifndef CCR_B200_H_
 #define CCR_B200_H_
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CCR_ABI_VERSION 4
+#define CCR_ABI_VERSION 5
 
 /* error codes */
 #define CCR_OK 0
@@ -55,6 +58,14 @@ extern "C" {
 #define CCR_FLAG_ALLOW_SHORT 0x10 /* k > n_items allowed: tail padded with (-inf, id -1); used for
                                      row shards smaller than k                                  */
 
+#define CCR_FLAG_PACKED_KEYS 0x20 /* out_scores64 receives uint64 sort keys instead of doubles:
+                                       (ord32(float32 score) << 32) | (0xFFFFFFFF - uint32 global id),
+                                       ord32(f) = bits(f) ^ (f < 0 ? 0xFFFFFFFF : 0x80000000); a larger key
+                                       ranks first (score descending, then id ascending), 0 = padding.  The
+                                       8-byte exchange format of the row-sharded path (ccr_merge_topk_keys);
+                                       needs id_offset + n_items <= 2^32 and no CCR_MASK_ADD (float64
+                                       priors do not fit a float32 key)                           */
+
 #define CCR_MAX_K 2048
 
 int ccr_abi_version(void);
@@ -77,7 +88,10 @@ const char* ccr_last_error_string(void);
  *   k        1 .. CCR_MAX_K
  *   mask_*   CSR over the LOCAL item columns of this shard: indptr[B+1] (int64), cols sorted
  *            and unique per row (int32, < n_items), vals float64, mask_nnz == indptr[B];
- *            mask_max_row_nnz = largest number of entries in one row (lets the kernel stream masked
+ *            (mask_nnz may also be an UPPER BOUND of indptr[B] -- the capacity of cols / vals -- when
+ *            the CSR was produced on the device, e.g. by ccr_mask_column_shard; the kernels read the
+ *            true count from indptr, the bound sizes the workspace);
+ *            mask_max_row_nnz = largest number of entries in one row, or an upper bound (lets the kernel stream masked
  *            items through and drop them at the end instead of testing every candidate; pass -1 if
  *            unknown); all NULL / 0 when mask_mode == CCR_MASK_NONE
  *   id_offset added to local item ids on output (row-sharded tables)
@@ -110,6 +124,26 @@ size_t ccr_score_topk_workspace_bytes(int64_t B, int64_t n_items, int D, int k,
 int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B, int k_in,
                    int k_out, float* out_scores, double* out_scores64, int64_t* out_ids,
                    void* stream);
+
+/*
+ * The same merge for runs in the packed exchange format of CCR_FLAG_PACKED_KEYS:
+ *   keys [G, B, k_in] uint64, each run sorted descending (0 = padding).  Output: out_scores
+ *   float32 [B, k_out] (may be NULL), out_ids int64 [B, k_out] (global ids; -1 / -inf padding).
+ * One all-gather of 8 bytes per entry instead of two of 8; merge-path
+ * merges in shared memory.  G * k_in keys must fit shared memory (CCR_EUNSUPPORTED otherwise:
+ * G * k_in <= ~16 K).
+ */
+int ccr_merge_topk_keys(const uint64_t* keys, int G, int64_t B, int k_in, int k_out, float* out_scores,
+                        int64_t* out_ids, void* stream);
+
+/*
+ * Column shard of a device mask CSR for a row-sharded table: entries with col_lo <= col < col_hi,
+ * re-based to local columns (col - col_lo).  out_indptr [B+1]; out_cols / out_vals need room for
+ * every entry of the input (the shard's count is only known on the device: pass the input's nnz as
+ * mask_nnz upper bound to ccr_score_topk_bf16).  Replaces a host-side numpy pass per step.
+ */
+int ccr_mask_column_shard(const int64_t* indptr, const int32_t* cols, const double* vals, int64_t B, int64_t col_lo,
+                          int64_t col_hi, int64_t* out_indptr, int32_t* out_cols, double* out_vals, void* stream);
 
 /*
  * Embedding-table ingest: fp32 rows -> bf16 table rows, optionally L2-normalised first
@@ -199,9 +233,28 @@ int ccr_choose_algo(int64_t B, int64_t n_items, int D, int k);
  */
 void ccr_set_profile_events(void* start_event, void* stop_event);
 
-/* Launch geometry of the last-configured plan, for benchmarks / DESIGN.md bookkeeping:
- * fills n_q_tiles, n_splits, cand_capacity, n_launches.  Returns 0 or CCR_E*. */
-int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int flags, int32_t* info4);
+/* Launch plan ccr_score_topk_bf16 would use for these arguments, for benchmarks / DESIGN.md
+ * bookkeeping.  Fills info8 = { n_q_tiles (units of 128 query rows, or 256 for CTA pairs), n_splits
+ * (item splits), cand_capacity (keys per candidate buffer), algo (CCR_ALGO_*), two_cta (0/1),
+ * seed_items (sampled items of the threshold-seeding pre-pass, 0 = none), n_kernel_launches (kernels
+ * one call launches), prefetch_tiles (L2 look-ahead distance) }.  Returns 0 or CCR_E*. */
+int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int64_t mask_max_row_nnz,
+                  int flags, int32_t* info8);
+
+/*
+ * Watchdog record.  Every barrier wait of the tensor-core kernel is bounded (10 s); on expiry the
+ * kernel writes { code = 1, where (role / barrier id), block, extra } and traps, which poisons the
+ * CUDA context -- device memory can no longer be read back.  A caller that wants the record passes a
+ * 16-byte HOST buffer that the device can write (cudaHostAlloc / pinned memory under UVA), zeroed;
+ * after a failed synchronisation it reads the four int32 from host memory.  NULL (default): the
+ * record goes to a slot inside the workspace.  Process-wide.
+ */
+void ccr_set_status_record(void* host_mapped_ptr);
+
+/* Diagnostics: re-read the CCR_* environment knobs.  They are parsed once on
+ * first use; an A/B harness that changes the environment of a live process calls this afterwards.
+ * Not thread-safe against concurrent ccr_* calls. */
+void ccr_debug_reload_env(void);
 
 #ifdef __cplusplus
 }

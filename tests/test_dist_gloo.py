@@ -118,6 +118,8 @@ def _worker_ranking(rank, world, port, ret):
     engine.SparseMask = HostMask
 
     class CpuIndex(cdist.ShardedIndex):
+        packed_calls = 0
+
         def _make_table(self, capacity, dim, normalize):
             self.rows_seen = []
             return None
@@ -139,6 +141,27 @@ def _worker_ranking(rank, world, port, ret):
             pad_s = torch.full((q.shape[0], kk - kl), float("-inf"), dtype=torch.float64)
             pad_i = torch.full((q.shape[0], kk - kl), -1, dtype=torch.int64)
             return torch.cat([s.double(), pad_s], 1), torch.cat([i, pad_i], 1)
+
+        # packed exchange (block masks are SET -1e6: float32-exact): keys exactly as the ABI defines them
+        def _local_topk_keys(self, q, kk, mask):
+            d, i = self._local_topk(q, kk, mask)
+            f = d.float().numpy().view(np.uint32).astype(np.uint64)
+            o = np.where(f >> 31, f ^ 0xFFFFFFFF, f | 0x80000000)
+            keys = (o << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - i.numpy().astype(np.uint64))
+            keys = np.where(i.numpy() >= 0, keys, np.uint64(0))
+            CpuIndex.packed_calls += 1
+            return torch.as_tensor(keys.view(np.int64))
+
+        def _merge_keys(self, keys, kk):
+            G, Bq, kin = keys.shape
+            flat = np.ascontiguousarray(keys.permute(1, 0, 2).reshape(Bq, G * kin).numpy()).view(np.uint64)
+            top = np.ascontiguousarray(np.sort(flat, axis=1)[:, ::-1][:, :kk])  # descending
+            o = (top >> np.uint64(32)).astype(np.uint32)
+            f = np.where(o >> 31, o & 0x7FFFFFFF, ~o).astype(np.uint32).view(np.float32)
+            ids = (np.uint64(0xFFFFFFFF) - (top & np.uint64(0xFFFFFFFF))).astype(np.int64)
+            ids = np.where(top == 0, -1, ids)
+            f = np.where(top == 0, -np.inf, f).astype(np.float32)
+            return torch.as_tensor(f), torch.as_tensor(ids)
 
         def _merge(self, scores64, ids, kk):
             G, Bq, kin = scores64.shape
@@ -166,6 +189,7 @@ def _worker_ranking(rank, world, port, ret):
     # the encoder saw every query batch plus only this rank's share of the corpus
     n = len(c["corpus"])
     lo, hi = cdist.shard_bounds(n, world, rank)
+    ok &= CpuIndex.packed_calls > 0  # the SET -1e6 block mask takes the one-gather packed exchange
     ret[rank] = (bool(ok), table.calls, -(-len(c["queries"]) // c["batch_size"]) + -(-(hi - lo) // c["batch_size"]))
     dist.barrier()
     dist.destroy_process_group()

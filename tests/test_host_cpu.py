@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().ccr_abi_version() == _lib.ABI_VERSION == 4
+    assert _lib.lib().ccr_abi_version() == _lib.ABI_VERSION == 5
 
 
 def test_planning_entry_points_work_without_gpu():
@@ -42,7 +42,26 @@ def test_planning_entry_points_work_without_gpu():
     assert L.ccr_choose_algo(512, 1000, 768, 10) == _lib.ALGO_TCGEN05
     info = _lib.plan_info(4096, 8841823, 768, 100)
     assert info["n_q_tiles"] == 16 and info["cand_capacity"] == 384 and info["n_splits"] >= 5  # 16 CTA-pair tiles
+    assert info["two_cta"] == 1 and info["seed_items"] > 0 and info["n_kernel_launches"] == 4
+    masked = _lib.plan_info(4096, 8841823, 768, 100, mask_nnz=30000, mask_max_row_nnz=64)
+    assert masked["n_kernel_launches"] == 5 and masked["cand_capacity"] == 512  # + override kernel; k + 64 kept
     assert _lib.plan_info(384, 8841823, 768, 100)["n_q_tiles"] == 3  # odd tile count: single CTAs
+
+
+def test_env_knobs_are_parsed_once_and_reloadable():
+    from ccr_b200 import _lib
+
+    base = _lib.plan_info(512, 8841823, 768, 100)
+    assert base["two_cta"] == 1
+    os.environ["CCR_2CTA"] = "0"
+    try:
+        assert _lib.plan_info(512, 8841823, 768, 100)["two_cta"] == 1   # cached knobs: no effect yet
+        _lib.reload_env()
+        assert _lib.plan_info(512, 8841823, 768, 100)["two_cta"] == 0
+    finally:
+        del os.environ["CCR_2CTA"]
+        _lib.reload_env()
+    assert _lib.plan_info(512, 8841823, 768, 100) == base
 
 
 def test_product_refuses_cpu_tensors():
