@@ -402,10 +402,12 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
 
   if (pl.algo == CCR_ALGO_TCGEN05 && B < kQTile && n_items > 0 && !kn.no_qpad) {
     // short batch: stage the queries in a [128, D] block so that no TMA box of the query operand is
-    // out of bounds (measurably faster than hardware zero-fill of 120+ rows).  Rows >= B of the block
-    // keep whatever the workspace held: MMA rows are independent and padding rows never select.
+    // out of bounds (measurably faster than hardware zero-fill of 120+ rows); only the padding rows
+    // are zeroed
     __nv_bfloat16* qp = (__nv_bfloat16*)(ws + pl.off_qpad);
-    e = cudaMemcpy2DAsync(qp, (size_t)D * 2, q, (size_t)ldq * 2, (size_t)D * 2, (size_t)B, cudaMemcpyDeviceToDevice, st);
+    e = cudaMemsetAsync(qp + (size_t)B * D, 0, (size_t)(kQTile - B) * D * sizeof(__nv_bfloat16), st);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(qp, (size_t)D * 2, q, (size_t)ldq * 2, (size_t)D * 2, (size_t)B, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail(CCR_ECUDA, "query padding: %s", cudaGetErrorString(e));
     sp.q = qp; sp.ldq = D; sp.q_rows = kQTile;
   }

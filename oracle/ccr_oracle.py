@@ -31,7 +31,8 @@ non-importable al_0_rank.py, executes its statements read from the file -- and s
 the outputs in tests/golden/*.npz; tests/test_oracle_golden.py and
 tests/test_al_rank_cpu.py replay them).
 
-``score_topk_ref`` is the arbiter for the CUDA kernels: fp32 (or fp64 when an
+``score_topk_ref`` (and ``score_topk_ref_device``, the same arithmetic with stock torch fp32 ops
+on the GPU so that the full 8.84 M-row shapes finish in seconds) is the arbiter for the CUDA kernels: fp32 (or fp64 when an
 additive float64 prior is present, as in the reference) scores from the
 *bf16-rounded* inputs, chunked over the corpus with a running top-k so it scales,
 ties broken by lowest id.  ``check_topk`` implements the tolerance rule of
@@ -76,12 +77,24 @@ def generate_embeddings_ref(data_indices, data_dic, embedding_func, batch_size):
     return torch.vstack(out)
 
 
+def _autocast_fp16_mm(a, b_t):
+    """What ``a @ b_t`` / ``torch.mm`` compute for CUDA tensors under ``torch.cuda.amp.autocast()``
+    (scripts/al_0_rank.py:125 wraps the ranking call in it): operands cast to fp16, products
+    accumulated in fp32 by the tensor cores, result rounded to fp16 -- restated with CPU fp32 ops.
+    The accumulation order of cuBLAS is not reproduced, so a result may differ from the GPU's by one
+    fp16 ulp when the fp32 sum falls next to a rounding boundary."""
+    return (a.half().float() @ b_t.half().float()).half().float()
+
+
 def ranking_ref(corpus, queries, embedding_func, batch_size, block_dict=None, sim_type=None,
-                topn=RANKING_TOPN, stable=True):
+                topn=RANKING_TOPN, stable=True, autocast_fp16=False):
     """scripts/ms_marco_eval.py:189-235 with its four CUDA calls removed.
 
     ``stable=True`` makes the per-row sort stable (ties -> lowest corpus position first),
     which is one of the orders the reference's unstable ``sort`` may legally produce.
+    ``autocast_fp16=True`` restates the reference's REAL GPU arithmetic (fp16 autocast matmul,
+    fp32 normalisation, scores stored back into the fp32 host matrix); pinned by
+    tests/golden/ranking_cuda_autocast_*.npz, produced by the unmodified function on a B200.
     """
     import pandas as pd
 
@@ -96,7 +109,12 @@ def ranking_ref(corpus, queries, embedding_func, batch_size, block_dict=None, si
     ranking_matrix = torch.zeros(num_queries, num_passages)          # :204
     for step in range(math.ceil(num_passages / batch_size)):         # :206-218
         pb = passage_embeddings[step * batch_size : (step + 1) * batch_size]
-        if sim_type == "cos":
+        if autocast_fp16:
+            if sim_type == "cos":   # F.normalize stays fp32 under autocast, torch.mm runs in fp16
+                scores = _autocast_fp16_mm(normalize_rows_ref(queries_embeddings), normalize_rows_ref(pb).T)
+            else:
+                scores = _autocast_fp16_mm(queries_embeddings, pb.T)
+        elif sim_type == "cos":
             scores = cos_sim_ref(queries_embeddings, pb)
         else:
             scores = queries_embeddings @ pb.T
@@ -403,6 +421,72 @@ def score_topk_ref(Q, P, k, mask=None, mode=MASK_NONE, sim="dot", round_bf16=Tru
     if not return_f64:
         out_s = out_s.to(torch.float32)
     return out_s, best_i + id_offset
+
+
+def score_topk_ref_device(Qe, Pe, k, mask=None, mode=MASK_NONE, chunk=1 << 17, id_offset=0, n_items=None):
+    """``score_topk_ref`` at full corpus sizes: the same arithmetic (fp32 products of the
+    bf16-rounded inputs, float64 where an additive prior is present, running top-k, ties -> lowest
+    id) evaluated chunk by chunk with stock torch ops on the device the ENCODED operands live on.
+
+    ``Qe`` [B, >=D], ``Pe`` [N, >=D]: the encoded (bf16-representable) queries / table rows, any
+    float dtype; they are widened to fp32 per chunk and multiplied with TF32 disabled, so this is an
+    fp32 reference of the kernels' bf16 x bf16 -> fp32 contraction, independent of them.
+    Returns (scores float32 | float64 for MASK_ADD, ids int64) on the CPU.
+    """
+    dev = Qe.device
+    B = Qe.shape[0]
+    N = Pe.shape[0] if n_items is None else int(n_items)
+    if k > N:
+        raise RuntimeError("selected index k out of range")
+    use64 = mode == MASK_ADD
+    dt = torch.float64 if use64 else torch.float32
+    old_tf32 = torch.backends.cuda.matmul.allow_tf32
+    old_prec = torch.get_float32_matmul_precision()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    try:
+        Qf = Qe.float()
+        m_r = m_c = m_v = None
+        if mask is not None and mode != MASK_NONE:
+            indptr, cols, vals = canonical_mask(mask[0], mask[1], mask[2], N, mode)
+            m_r = torch.as_tensor(np.repeat(np.arange(B, dtype=np.int64), np.diff(indptr)), device=dev)
+            m_c = torch.as_tensor(cols.astype(np.int64), device=dev)
+            m_v = torch.as_tensor(vals, dtype=dt, device=dev)
+        best_s = torch.empty((B, 0), dtype=dt, device=dev)
+        best_i = torch.empty((B, 0), dtype=torch.int64, device=dev)
+        for s0 in range(0, N, chunk):
+            s1 = min(N, s0 + chunk)
+            sc = (Qf @ Pe[s0:s1].float().T).to(dt)
+            if m_c is not None:
+                sel = (m_c >= s0) & (m_c < s1)
+                r, c, v = m_r[sel], m_c[sel] - s0, m_v[sel]
+                if mode == MASK_SET:
+                    sc[r, c] = v
+                else:
+                    sc[r, c] = sc[r, c] + v
+            kk = min(k, s1 - s0)
+            tv, ti = torch.topk(sc, kk, dim=1, sorted=True)
+            # torch.topk does not promise the LOWEST ids among values tied with its kk-th: rows where
+            # the chunk holds more copies of that value than were selected are redone by a stable sort
+            vk = tv[:, -1:]
+            redo = torch.nonzero((sc == vk).sum(1) != (tv == vk).sum(1)).flatten()
+            if redo.numel():
+                o = torch.sort(sc[redo], dim=1, descending=True, stable=True)
+                tv[redo], ti[redo] = o.values[:, :kk], o.indices[:, :kk]
+            cat_s = torch.cat([best_s, tv], dim=1)
+            cat_i = torch.cat([best_i, ti + s0], dim=1)
+            # order by (score descending, id ascending): sort by id, then a stable sort by score
+            o1 = torch.sort(cat_i, dim=1, stable=True)
+            cat_s = torch.gather(cat_s, 1, o1.indices)
+            o2 = torch.sort(cat_s, dim=1, descending=True, stable=True)
+            keep = min(k, cat_s.shape[1])
+            best_s = o2.values[:, :keep].contiguous()
+            best_i = torch.gather(o1.values, 1, o2.indices[:, :keep]).contiguous()
+            del sc, tv, ti
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
+        torch.set_float32_matmul_precision(old_prec)
+    return best_s.cpu(), (best_i + id_offset).cpu()
 
 
 def full_scores_ref(Q, P, mask=None, mode=MASK_NONE, sim="dot", round_bf16=True):

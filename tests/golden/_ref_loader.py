@@ -17,7 +17,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = "/root/reference"
+# /root/reference in the build container; tests/golden/make_golden_cuda.py points this at the staged,
+# git-ignored copy under baseline/_ref/ that travels to the GPU box
+REFERENCE_ROOT = os.path.abspath(os.environ.get("CCR_REFERENCE_ROOT", "/root/reference"))
 
 
 def reference_available():

@@ -37,7 +37,7 @@ class TextTable:
 
 def ranking_case(name):
     """-> dict(corpus, queries, table, batch_size, block_dict, sim_type)."""
-    spec = RANKING_CASES[name]
+    spec = RANKING_CASES[name] if name in RANKING_CASES else CUDA_RANKING_CASES[name]
     n, q, d = spec["n"], spec["q"], spec["d"]
     same = spec.get("queries_are_corpus", False)
     emb = embeddings(spec["seed"], n if same else n + q, d, spec.get("clustered", False))
@@ -70,6 +70,17 @@ RANKING_CASES = {
     # heavy blocking: fewer than 1001 unmasked items for some rows -> -1e6 entries are returned
     "dot_block_tail_n1100": dict(seed=14, n=1100, q=10, d=64, sim="dot", batch_size=256, brands=5,
                                  queries_are_corpus=True),
+}
+
+
+# cases run through the UNMODIFIED reference ranking() with real .cuda() calls under
+# torch.cuda.amp.autocast() on a B200 (tests/golden/make_golden_cuda.py)
+CUDA_RANKING_CASES = {
+    "dot_d768_n5000": dict(seed=21, n=5000, q=24, d=768, sim="dot", batch_size=512),
+    "cos_block_d768_n4000": dict(seed=22, n=4000, q=20, d=768, sim="cos", batch_size=512, brands=30,
+                                 queries_are_corpus=True, clustered=True),
+    "dot_block_d64_n3000": dict(seed=23, n=3000, q=16, d=64, sim="dot", batch_size=256, brands=12,
+                                queries_are_corpus=True),
 }
 
 

@@ -1,0 +1,27 @@
+"""Row-sharded search on 2 / 4 / 8 GPUs of one box against the fp32 device oracle and the single-table
+result (tests/dist_check.py under torchrun, one process per GPU, NCCL).  Skipped where fewer than two
+GPUs are visible; the N = 1 paths of the same code are covered by test_gpu_fullsize.py."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_search_matches_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, {torch.cuda.device_count()} visible")
+    port = 29700 + world + os.getpid() % 100
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, tail
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rank ")]
+    assert len(lines) >= 7 * world and all("equal_single_table=True oracle_violations=0" in ln for ln in lines), tail
