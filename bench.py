@@ -1,18 +1,24 @@
 #!/usr/bin/env python3
 """Benchmark of the score-and-rank hot path (contract: see the task prompt / DESIGN.md §Measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config marco|c5] [--batch B]
 
 One "step" = one pass of the hot path over one batch of B synthetic queries: fused
-score(Q . P^T) -> history mask (set -1e6) -> per-row top-100 over the MS-MARCO-shaped corpus
-(8,841,823 x 768 bf16, BASELINE.json configs[2], the configuration the metric is quoted on; it fits
-one B200).  With N > 1 the corpus is row-sharded across the ranks (strong scaling: the corpus is
-fixed), every rank computes its local top-k, one all-gather of (float64 score, int64 id) pairs is
-followed by an on-device G-way merge.
+score(Q . P^T) -> history mask (set -1e6) -> per-row top-k.
+
+--config marco (default; BASELINE.json configs[2], the configuration the metric is quoted on; fits one
+    B200): 8,841,823 x 768 bf16 corpus, top-100.  With N > 1 the corpus is row-sharded (strong scaling:
+    the corpus is fixed).
+--config c5 (BASELINE.json configs[4]): 100,000,000 x 768 bf16 row-sharded over the ranks (19.2 GB each at
+    8 GPUs; needs >= 8 GPUs of 180 GB -- or 1 GPU for a single 12.5 M-row shard with --n-items), top-1000.
+
+With N > 1 every rank computes its local top-k, ONE all-gather of packed 8-byte (float32 score, uint32
+global id) keys is followed by an on-device G-way merge-path merge.
 
 value  : queries/s, whole job, inputs (bf16 table shard, bf16 queries, mask CSR) resident in HBM.
-e2e    : the same through the public host API from HOST buffers: pinned fp32 queries + mask CSR are
-         copied H2D, encoded to bf16, searched, and the [B,k] scores+ids are copied back D2H inside
+e2e    : the same through the public host API from HOST buffers: pinned fp32 queries (each rank uploads
+         and encodes 1/G of the rows, all-gathered over NVLink) + the mask CSR are copied H2D, the mask
+         is column-sharded on the device, and rank 0 copies the [B,k] scores + ids back D2H, all inside
          the timed region.
 """
 import argparse
@@ -29,9 +35,18 @@ sys.path.insert(0, os.path.join(ROOT, "crowd-coachable-recommendations_b200"))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "queries/s, top-100 over 8.8M x 768 corpus"
 N_ITEMS, DIM, TOPK = 8_841_823, 768, 100
 CHUNK = 1 << 20
+CONFIGS = {
+    "marco": dict(n_items=N_ITEMS, k=100, batch=4096,
+                  metric="queries/s, top-100 over 8.8M x 768 corpus",
+                  workload="MS-MARCO-shape retrieval (BASELINE.json configs[2]): 8,841,823 x 768 bf16 corpus, "
+                           "top-100 with history mask (set -1e6, nnz/row ~ min(Geom(1/8),64))"),
+    "c5": dict(n_items=100_000_000, k=1000, batch=4096,
+               metric="queries/s, top-1000 over 100M x 768 corpus row-sharded across the GPUs",
+               workload="BASELINE.json configs[4]: synthetic 100,000,000 x 768 bf16 item table row-sharded across "
+                        "the ranks, top-1000 with history mask, packed all-gather + on-device merge"),
+}
 
 
 def parse():
@@ -40,11 +55,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096, help="queries per step")
-    ap.add_argument("--n-items", type=int, default=N_ITEMS)
-    ap.add_argument("--k", type=int, default=TOPK)
+    ap.add_argument("--config", default="marco", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="queries per step (default: the config's)")
+    ap.add_argument("--n-items", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-library-baseline", action="store_true")
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.custom_shape = a.n_items is not None or a.k is not None
+    a.batch = a.batch or cfg["batch"]
+    a.n_items = a.n_items or cfg["n_items"]
+    a.k = a.k or cfg["k"]
+    a.metric = cfg["metric"] if not a.custom_shape else f"queries/s, top-{a.k} over {a.n_items} x {DIM} corpus"
+    a.workload = cfg["workload"] if not a.custom_shape else (
+        f"custom shape: {a.n_items} x {DIM} bf16 corpus, top-{a.k} with history mask")
+    return a
 
 
 def peaks():
@@ -54,6 +80,17 @@ def peaks():
         return dict(tflops=p.get("bf16_tflops_sustained", 1401.9), tflops_burst=p.get("bf16_tflops", 1667.8),
                     hbm=p.get("hbm_gbs", 6445.3), source="measured (MEASURED_PEAKS.json)")
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel on a named workload, from the committed ncu capture
+    (profiles/traffic.json: {key: {"dram_bytes": read + write, "source": file}}); None when no capture of
+    this exact workload exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    ent = json.load(open(path)).get(key)
+    return (ent["dram_bytes"], ent["source"]) if ent else (None, None)
 
 
 def history_mask_rows(B, n_items, seed=2):
@@ -70,56 +107,88 @@ def rows_to_csr(rows):
 
 
 # ----------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's own CPU path (oracle port), bounded sample
+# reference arm / CPU baseline: the reference's own CPU path (oracle port)
 # ----------------------------------------------------------------------------------------------
-def cpu_reference_step(sample_items, sample_queries, seed=0):
+def host_corpus(n_items, seed=0):
+    """fp32 host corpus of the workload's shape for the CPU legs.  One seeded 1 Mi-row normal block is
+    drawn and repeated with a per-copy scale (distinct rows, normal-like scores): drawing 6.8 G normals
+    with the serial CPU generator would take longer than the measurement."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn((min(n_items, CHUNK), DIM), generator=g)
+    if n_items <= CHUNK:
+        return base
+    P = torch.empty((n_items, DIM))
+    for c, s in enumerate(range(0, n_items, CHUNK)):
+        e = min(n_items, s + CHUNK)
+        torch.mul(base[: e - s], 1.0 + 1e-3 * c, out=P[s:e])
+    return P
+
+
+def cpu_reference_step(P, n_queries, seed=0):
     from oracle import ccr_oracle as O
 
-    g = torch.Generator().manual_seed(seed)
-    P = torch.randn((sample_items, DIM), generator=g)
-    Q = torch.randn((sample_queries, DIM), generator=g)
-    rows = history_mask_rows(sample_queries, sample_items, seed=2)
+    g = torch.Generator().manual_seed(100 + seed)
+    Q = torch.randn((n_queries, DIM), generator=g)
+    rows = history_mask_rows(n_queries, P.shape[0], seed=2)
     t0 = time.perf_counter()
     O.ranking_core_ref(Q, P, batch_size=512, block_rows=rows, sim_type="dot")
     return time.perf_counter() - t0
 
 
+REF_WHAT = ("oracle.ranking_core_ref (ms_marco_eval.py:203-230 on CPU: fp32 tile matmul batch 512 -> host QxN matrix "
+            "-> -1e6 block mask -> full per-row sort -> top 1001)")
+
+
 def cpu_baseline(n_items, sample_items=1 << 20, sample_queries=96):
-    dt = cpu_reference_step(sample_items, sample_queries)
+    """Bounded sample for the `ours` line (10-30 s of CPU work): full embedding width, a 1 Mi-row slice of
+    the corpus, scaled linearly in the corpus length (`--impl reference` runs the real length)."""
+    dt = cpu_reference_step(host_corpus(sample_items), sample_queries)
     qps_sample = sample_queries / dt
     return {
         "value": qps_sample * sample_items / n_items,
         "unit": "queries/s",
         "cores": torch.get_num_threads(),
         "kind": "port",
-        "sample": (f"oracle.ranking_core_ref (ms_marco_eval.py:203-230 on CPU: fp32 tile matmul batch 512 -> host "
-                   f"QxN matrix -> -1e6 block mask -> full per-row sort -> top 1001) on {sample_queries} queries x "
-                   f"{sample_items} items x {DIM}: {dt:.2f} s = {qps_sample:.2f} q/s, scaled linearly by "
-                   f"{sample_items}/{n_items} to the full corpus; os.cpu_count()={os.cpu_count()}, "
-                   f"affinity={len(os.sched_getaffinity(0))}"),
+        "sample": (f"{REF_WHAT} on {sample_queries} queries x {sample_items} items x {DIM}: {dt:.2f} s = "
+                   f"{qps_sample:.2f} q/s, scaled linearly by {sample_items}/{n_items} to the full corpus; "
+                   f"os.cpu_count()={os.cpu_count()}, affinity={len(os.sched_getaffinity(0))}"),
     }
 
 
 def run_reference(args):
+    """The reference's CPU implementation of the path at the workload's REAL corpus length (host fp32 table:
+    27.2 GB for 8,841,823 x 768) on a bounded number of queries per step; falls back to a corpus sample
+    only if the host cannot hold the table."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_items, sample_queries = 1 << 20, 96
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_reference_step(sample_items, 4)
-    times = [cpu_reference_step(sample_items, sample_queries, seed=i) for i in range(max(1, min(args.steps, 3)))]
+    n_queries = 32
+    n_ref, scale, note = args.n_items, 1.0, "full corpus length"
+    try:
+        if args.n_items * DIM * 4 > 64 << 30:
+            raise MemoryError("corpus above 64 GB of host fp32")
+        P = host_corpus(args.n_items)
+    except (MemoryError, RuntimeError) as e:  # host too small: bounded corpus sample, scaled linearly
+        n_ref = 1 << 20
+        scale = n_ref / args.n_items
+        note = f"host could not hold the corpus ({type(e).__name__}): {n_ref}-row sample scaled linearly"
+        P = host_corpus(n_ref)
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_reference_step(P, 2)
+    times = [cpu_reference_step(P, n_queries, seed=i) for i in range(max(1, min(args.steps, 2)))]
     dt = float(np.median(times))
-    qps = sample_queries / dt * sample_items / args.n_items
+    qps = n_queries / dt * scale
     line = {
-        "impl": "reference", "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": args.metric, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MS-MARCO-shape retrieval: 8,841,823 x 768, top-100 with history mask (reference "
-                               "CPU path keeps its top-1001 slice)", "n_items": args.n_items, "dim": DIM,
-                   "k": args.k, "sample_items": sample_items, "sample_queries": sample_queries},
+        "config": {"workload": args.workload + " (the reference's CPU path keeps its top-1001 slice)",
+                   "n_items": args.n_items, "dim": DIM, "k": args.k, "queries_per_step": n_queries,
+                   "reference_corpus_rows": n_ref, "note": note},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample_queries} queries x {sample_items} items per step, scaled linearly to "
-                                   f"{args.n_items} items"},
+                         "sample": f"{REF_WHAT}: {n_queries} queries x {n_ref} items per step ({note}); "
+                                   f"os.cpu_count()={os.cpu_count()}, affinity={len(os.sched_getaffinity(0))}"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -186,6 +255,37 @@ def build_shard(table, lo, hi, dev):
         del rows
 
 
+def library_baseline(table, q_dev, k, steps=2, chunk=1 << 17):
+    """The library-call GPU implementation of the same step on the same box (context): stock
+    torch bf16 ``Q @ P_chunk.T`` (cuBLAS) + ``torch.topk`` per chunk + a final merge.  No mask (it would
+    only add work); ranks bf16-rounded scores.  Timed with CUDA events after one warm-up step."""
+    items, n = table.data, len(table)
+
+    def step():
+        best_s, best_i = [], []
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            v, i = (q_dev @ items[s:e].T).topk(min(k, e - s), dim=1)
+            best_s.append(v)
+            best_i.append(i + s)
+        v, i = torch.cat(best_s, 1), torch.cat(best_i, 1)
+        top, pos = v.topk(k, dim=1)
+        return top, torch.gather(i, 1, pos)
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": q_dev.shape[0] / ms * 1e3, "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+            "what": f"torch bf16 Q@P_chunk.T (cuBLAS) + torch.topk per {chunk}-row chunk + merge, no mask, this GPU's "
+                    "shard only"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -203,21 +303,21 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B, N, k = args.batch, args.n_items, args.k
     pk = peaks()
+    shard_rows = -(-N // world)
+    if shard_rows * DIM * 2 > 170e9:
+        raise RuntimeError(f"--config {args.config}: a shard of {shard_rows} rows ({shard_rows * DIM * 2 / 1e9:.1f} GB) "
+                           f"does not fit one B200; run it on more GPUs (c5 is defined on 8)")
 
     # ---- resident state: table shard, queries, mask ----
-    if world > 1:
-        index = ccr_b200.ShardedIndex(N, DIM, device=dev)
-        table, lo, hi = index.table, index.lo, index.hi
-    else:
-        index, lo, hi = None, 0, N
-        table = ccr_b200.EmbeddingTable(N, DIM, device=dev)
+    index = ccr_b200.ShardedIndex(N, DIM, device=dev)     # world == 1: one shard holding everything
+    table, lo, hi = index.table, index.lo, index.hi
     build_shard(table, lo, hi, dev)
     gq = torch.Generator().manual_seed(7)
     q_host = torch.randn((B, DIM), generator=gq).pin_memory()
     rows = history_mask_rows(B, N)
     indptr, cols, vals = rows_to_csr(rows)
     mask_global = engine.SparseMask(indptr, cols, vals, N, engine.MASK_SET, dev)
-    mask_local = mask_global.column_shard(lo, hi) if world > 1 else mask_global
+    mask_local = mask_global.column_shard_device(lo, hi) if world > 1 else mask_global
     q_dev = table.encode_queries(q_host)
     pin = {n: torch.as_tensor(a).pin_memory() for n, a in (("indptr", indptr), ("cols", cols), ("vals", vals))}
     out_s_host = torch.empty((B, k), dtype=torch.float32).pin_memory()
@@ -225,26 +325,24 @@ def run_ours(args):
 
     def step_resident():
         if world > 1:
-            d, i = index._local_topk(q_dev, k, mask_local)
-            gs = torch.empty((world * B, k), dtype=d.dtype, device=dev)
-            gi = torch.empty((world * B, k), dtype=i.dtype, device=dev)
-            dist.all_gather_into_tensor(gs, d)
-            dist.all_gather_into_tensor(gi, i)
-            return engine.merge_topk(gs.view(world, B, k), gi.view(world, B, k), k)[:2]
+            keys = index._local_topk_keys(q_dev, k, mask_local)
+            gk = torch.empty((world * B, k), dtype=keys.dtype, device=dev)
+            dist.all_gather_into_tensor(gk, keys)
+            return engine.merge_topk_keys(gk.view(world, B, k), k)
         return table.search(q_dev, k, mask=mask_local, encoded=True)
 
     def step_e2e():
-        qd = q_host.to(dev, non_blocking=True)
         m = engine.SparseMask.from_device_tensors(pin["indptr"].to(dev, non_blocking=True),
                                                   pin["cols"].to(dev, non_blocking=True),
                                                   pin["vals"].to(dev, non_blocking=True), (indptr, cols, vals), N,
-                                                  engine.MASK_SET)
+                                                  engine.MASK_SET, f32_exact=True)
         if world > 1:
-            s, i, _ = index.search(qd, k, mask=m)
+            s, i, _ = index.search(q_host, k, mask=m)   # host queries: 1/G uploaded per rank + all-gather
         else:
-            s, i = table.search(qd, k, mask=m)
-        out_s_host.copy_(s, non_blocking=True)
-        out_i_host.copy_(i, non_blocking=True)
+            s, i = table.search(q_host.to(dev, non_blocking=True), k, mask=m)
+        if rank == 0:
+            out_s_host.copy_(s, non_blocking=True)
+            out_i_host.copy_(i, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -280,7 +378,7 @@ def run_ours(args):
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(args.steps):
-        step_e2e()  # ends with a stream synchronize: the host has the step's [B,k] result
+        step_e2e()  # ends with a stream synchronize: rank 0's host has the step's [B,k] result
     g1.record()
     barrier()
     e2e_ms_total = g0.elapsed_time(g1)
@@ -294,36 +392,48 @@ def run_ours(args):
     e2e_value = B / (e2e_ms_total / args.steps) * 1e3
 
     n_local = hi - lo
+    clocks = clk.summary()
     flops = 2.0 * B * n_local * DIM            # algorithmic flops of one launch of the dominant kernel
-    achieved = flops / (kern_ms * 1e-3) / 1e12
-    plan = _lib.plan_info(B, n_local, DIM, k)
-    launches_per_step = 5 + (1 if world > 1 else 0)  # seed GEMM, seed select, fused select, mask overrides,
-                                                     # finalize (+ G-way merge); NCCL kernels not counted
+    hbm_bytes = float(n_local) * DIM * 2        # algorithmic bytes: the shard once
+    t_tensor, t_hbm = flops / (pk["tflops_burst"] * 1e12), hbm_bytes / (pk["hbm"] * 1e9)
+    plan = _lib.plan_info(B, n_local, DIM, k, mask_nnz=int(indptr[-1]), mask_max_row_nnz=mask_global.max_row_nnz)
+    launches_per_step = plan["n_kernel_launches"] + (1 if world > 1 else 0)   # + G-way merge; NCCL kernels not counted
+    # which cuBLAS peak the kernel is compared with: the sustained (power-capped) figure when the sampled
+    # clock shows the cap at work, the burst figure when the GPU ran un-capped
+    capped = "sw_power_cap" in clocks.get("reasons", []) or (clocks.get("sm_mhz") or 0) < 1600
+    if t_tensor >= t_hbm:
+        achieved = flops / (kern_ms * 1e-3) / 1e12
+        peak = pk["tflops"] if capped else pk["tflops_burst"]
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": pk["source"] + (", sustained cuBLAS bf16 (sw_power_cap active / clock below 1.6 GHz)"
+                                               if capped else ", burst cuBLAS bf16 (clock un-capped)"),
+                "frac_of_burst_peak": achieved / pk["tflops_burst"], "algorithmic_flops_per_launch": flops}
+    else:
+        achieved = hbm_bytes / (kern_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                "peak_source": pk["source"] + ", device copy bandwidth", "algorithmic_bytes_per_launch": hbm_bytes}
+    traffic, traffic_src = measured_traffic(f"{args.config}:B{B}:N{n_local}:k{k}:g{world}")
+    roof.update({"traffic": traffic, "traffic_source": traffic_src,
+                 "kernel": "select_tc_kernel (TMA + tcgen05 GEMM fused with mask + exact top-k)", "kernel_ms": kern_ms})
     line = {
-        "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "metric": args.metric, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "MS-MARCO-shape retrieval (BASELINE.json configs[2]): 8,841,823 x 768 bf16 corpus, "
-                               "top-100 with history mask (set -1e6, nnz/row ~ min(Geom(1/8),64))",
-                   "n_items": N, "dim": DIM, "k": k, "queries_per_step": B, "parallelism": f"row-shard x{world}",
-                   "l2": "inputs larger than L2 (13.6 GB table streamed every step)",
+        "config": {"workload": args.workload, "n_items": N, "dim": DIM, "k": k, "queries_per_step": B,
+                   "parallelism": f"row-shard x{world}",
+                   "l2": f"inputs larger than L2 ({hbm_bytes / 1e9:.1f} GB table shard streamed every step)",
                    "plan": plan},
-        "clocks": clk.summary(),
+        "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "queries/s",
-                "h2d_bytes_per_step": int(q_host.numel() * 4 + indptr.nbytes + cols.nbytes + vals.nbytes),
+                # per rank: its 1/G slice of the fp32 queries + the mask CSR; back: rank 0's [B,k] scores + ids
+                "h2d_bytes_per_step": int(-(-B // world) * DIM * 4 + indptr.nbytes + cols.nbytes + vals.nbytes),
                 "d2h_bytes_per_step": int(B * k * 12)},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops"],
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
-                     # exact workload (profiles/r01_select_tc_b4096_pairs_ncu_raw.csv: 16.98 GB read + 0.11 GB
-                     # written); algorithmic bytes = 13.58e9
-                     "traffic": 17.09e9 if (world == 1 and B == 4096 and N == N_ITEMS and k == TOPK) else None,
-                     "kernel": "select_tc_kernel (tcgen05 GEMM fused with mask + top-k)",
-                     "kernel_ms": kern_ms, "peak_source": pk["source"] + ", sustained cuBLAS bf16",
-                     "frac_of_burst_peak": achieved / pk["tflops_burst"],
-                     "algorithmic_flops_per_launch": flops},
+        "roofline": roof,
+        "step_roofline_frac_of_burst": max(t_tensor, t_hbm) * 1e3 / ms_step,
     }
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        line["gpu_library_baseline"] = library_baseline(table, q_dev, k)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(N)

@@ -12,7 +12,8 @@ Public surface (mirrors the reference's call sites for this path):
 * ``score_topk`` / ``merge_topk``                          (thin wrappers of the C ABI)
 """
 from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, MASK_ADD, MASK_NONE, MASK_SET, LIB_PATH  # noqa: F401
-from .engine import SparseMask, ingest_rows, merge_topk, score_dense, score_topk, topk_dense  # noqa: F401
+from .engine import (SparseMask, device_status, ingest_rows, merge_topk, merge_topk_keys, score_dense,  # noqa: F401
+                     score_topk, synchronize, topk_dense)
 from .table import EmbeddingTable  # noqa: F401
 from .score_array import (  # noqa: F401
     ElementWiseExpression,

@@ -128,7 +128,7 @@ def plan_info(B, n_items, D, k, flags=0, mask_nnz=0, mask_max_row_nnz=-1):
     arr = (ctypes.c_int32 * 8)()
     check(lib().ccr_plan_info(B, n_items, D, k, mask_nnz, mask_max_row_nnz, flags, arr))
     return {"n_q_tiles": arr[0], "n_splits": arr[1], "cand_capacity": arr[2], "algo": arr[3], "two_cta": arr[4],
-            "seed_items": arr[5], "n_kernel_launches": arr[6], "prefetch_tiles": arr[7]}
+            "seed_items": arr[5], "n_kernel_launches": arr[6], "lead_tiles": arr[7]}
 
 
 def reload_env():

@@ -22,9 +22,8 @@ namespace {
 struct Knobs {
   int mask_exclude = 0, two_cta = -1, split_mult = 0, cap_mult = 0, no_share = 0, no_seed = 0, no_hist = 0;
   long long seed_m = 0;
-  int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0, prefetch = -1;
+  int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0, l2_budget_mb = 0;
   float debug_tau = 0.f;
-  unsigned long long hint_q = 0, hint_items = 0;
 };
 Knobs g_knobs;
 std::once_flag g_knobs_once;
@@ -46,10 +45,8 @@ void load_knobs() {
   k.throttle = env_int("CCR_THROTTLE", -1);
   k.lead = env_int("CCR_LEAD", 0);
   k.no_qpad = getenv("CCR_NO_QPAD") != nullptr;
-  k.prefetch = env_int("CCR_PREFETCH", -1);
+  k.l2_budget_mb = env_int("CCR_L2_BUDGET_MB", 0);
   { const char* v = getenv("CCR_DEBUG_TAU"); k.debug_tau = v ? (float)atof(v) : 0.f; }
-  { const char* v = getenv("CCR_HINT_Q"); k.hint_q = v ? strtoull(v, nullptr, 0) : 0ull; }
-  { const char* v = getenv("CCR_HINT_ITEMS"); k.hint_items = v ? strtoull(v, nullptr, 0) : 0ull; }
   g_knobs = k;
 }
 const Knobs& knobs() {
@@ -106,7 +103,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int splits_tc(int nq, long long tiles, int sms) {
   long long smax = tiles < 1 ? 1 : tiles;
-  long long s0 = (sms + nq - 1) / nq;
+  long long s0 = sms / nq;  // from the largest split count that still fits ONE wave
   if (s0 < 1) s0 = 1;
   if (s0 >= smax) return (int)smax;
   long long best = s0;
@@ -219,6 +216,7 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
     const long long floor_m = (hist_ok ? 16LL : 64LL) * pl->k_keep;  // >= 2 k_keep groups of 8
     if (m < floor_m) m = floor_m;
     if (m < 4096) m = 4096;
+    m = (m + 255) / 256 * 256;  // whole tiles; rounding UP keeps m >= floor_m
     if (m > 131072) m = 131072;
     if (m > n_items / 8) m = n_items / 8;
     long long cap = 8LL * (512LL << 20) / (4LL * pl->rows_pad);
@@ -236,10 +234,22 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   return true;
 }
 
-// L2 look-ahead distance (item tiles) of the tensor-core kernel; 0 = off.  See SelectParams.
-int default_prefetch_tiles(const Plan& pl, long long B) {
-  (void)pl; (void)B;
-  return 0;
+// Bounded-drift lead (item tiles) of the units that stream one item split.  The tiles between the
+// slowest and the fastest unit of every split in flight must stay L2-resident or the followers re-read
+// them from HBM: (splits in flight) x lead x tile bytes is held to a budget well inside the 126 MB L2
+// (B=1024 at 8.84M x 768: 18.5 splits in flight x 16 tiles x 393 KB = 116 MB -> 24.6 GB of DRAM reads for
+// a 13.6 GB table, ncu profiles/r02_batch_counters.csv; with the budget: lead 4).
+int default_lead_tiles(const Plan& pl, int D, int sms) {
+  const int workers = pl.two_cta ? sms / 2 : sms;
+  long long conc = (workers + pl.n_q_tiles - 1) / pl.n_q_tiles;
+  if (conc > pl.S) conc = pl.S;
+  if (conc < 1) conc = 1;
+  const long long tile_bytes = (long long)kITile * D * 2;
+  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 32;
+  long long lead = ((long long)mb << 20) / (conc * tile_bytes);
+  if (lead > 16) lead = 16;
+  if (lead < 2) lead = 2;
+  return (int)lead;
 }
 
 int check_shape(long long B, long long n_items, int D, int k, int flags) {
@@ -296,8 +306,8 @@ int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, in
   Plan pl;
   make_plan(B, n_items, D, k, mask_nnz, mask_nnz > 0 ? mask_max_row_nnz : -1, flags, &pl);
   const bool seeded = pl.seed_m > 0 && n_items > 0 && !knobs().keep_tau;
-  int pf = pl.algo == CCR_ALGO_TCGEN05 ? default_prefetch_tiles(pl, B) : 0;
-  if (knobs().prefetch >= 0) pf = knobs().prefetch <= 64 ? knobs().prefetch : 64;
+  int lead = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl, D, device_sm_count()) : 0;
+  if (knobs().lead >= 1 && knobs().lead <= 4096) lead = knobs().lead;
   info8[0] = pl.n_q_tiles;
   info8[1] = pl.S;
   info8[2] = pl.C;
@@ -307,7 +317,7 @@ int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, in
   // kernels one ccr_score_topk_bf16 call launches: [seeding GEMM, seed select,] fused score+select,
   // [mask overrides,] finalize  (memsets / the short-batch query copy are not kernels of this library)
   info8[6] = (B > 0) ? (seeded ? 2 : 0) + (n_items > 0 ? 1 : 0) + (mask_nnz > 0 ? 1 : 0) + 1 : 0;
-  info8[7] = pf;
+  info8[7] = lead;
   return CCR_OK;
 }
 
@@ -359,20 +369,19 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.counts = (int*)(ws + pl.off_counts);
   sp.status = status;
   sp.debug = kn.debug; sp.debug_tau = kn.debug_tau; sp.debug_grid = kn.debug_grid;
-  sp.hint_q = kn.hint_q; sp.hint_items = kn.hint_items;
   sp.g_tau = nullptr; sp.g_q = nullptr; sp.S_row = pl.S * pl.halves; sp.share_j = pl.share_j; sp.share_m = pl.share_m;
   sp.dense_out = nullptr; sp.ld_out = 0; sp.store_max8 = 0;
   sp.progress = nullptr;
-  sp.prefetch_tiles = (pl.algo == CCR_ALGO_TCGEN05) ? default_prefetch_tiles(pl, B) : 0;
-  if (kn.prefetch >= 0) sp.prefetch_tiles = kn.prefetch <= 64 ? kn.prefetch : 64;
   sp.g_hist = nullptr; sp.g_hpar = nullptr;
   // bounded drift between the units that stream the same item split: default for CTA pairs (their
   // deeper pipeline lets a leader run away from its followers: 99 GB instead of 15 GB of DRAM reads
   // at B=4096), opt-in for single CTAs where it was measured to cost more than it saves
   bool use_throttle = pl.two_cta && pl.n_q_tiles > 1;
   if (kn.throttle >= 0) use_throttle = kn.throttle != 0;
-  sp.lead_tiles = 16;
+  sp.lead_tiles = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl, D, device_sm_count()) : 16;
   if (kn.lead >= 1 && kn.lead <= 4096) sp.lead_tiles = kn.lead;
+  sp.lead_every = 1;
+  while (sp.lead_every * 4 <= sp.lead_tiles && sp.lead_every < 8) sp.lead_every *= 2;  // 16 -> 8 (4 -> 2, 2 -> 1)
   if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) sp.progress = (int*)(ws + pl.off_progress);
   if (pl.share_j > 0 || pl.seed_m > 0) {
     sp.g_tau = (u32*)(ws + pl.off_gtau);
@@ -384,7 +393,7 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
     ss.n_items = pl.seed_m; ss.ldi = ldi * pl.seed_stride;
     ss.mask_indptr = nullptr; ss.mask_cols = nullptr;
     ss.dense_out = (float*)(ws + pl.off_seed); ss.ld_out = pl.seed_ld; ss.store_max8 = 1;
-    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr; ss.prefetch_tiles = 0;
+    ss.g_tau = nullptr; ss.g_q = nullptr; ss.share_j = 0; ss.progress = nullptr;
     // the histogram needs the seed bound as its origin and counts every streamed item, so it is
     // off in exclude-mask mode (masked items must not be counted)
     const bool use_hist = sp.mask_cols == nullptr && !kn.no_hist;

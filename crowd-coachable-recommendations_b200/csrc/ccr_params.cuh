@@ -54,14 +54,7 @@ struct SelectParams {
   // tiles L2-resident so the table is read from HBM once): tiles issued so far, per unit
   int* progress;  // [n_units], zeroed per call; null = off
   int lead_tiles; // max lead (item tiles) of a producer over the slowest unit on the same split
-  // L2 look-ahead: the units that stream one item split take turns issuing
-  // cp.async.bulk.prefetch.tensor for the tile `prefetch_tiles` ahead of their own position (each
-  // tile is requested once per split, by one unit), so the demand loads of every unit hit L2 and the
-  // bytes in flight towards HBM are no longer limited by the shared-memory ring.  0 = off.
-  int prefetch_tiles;
-  // L2 eviction-priority hints of the two operand streams (createpolicy-style 64-bit descriptors,
-  // 0 = none): diagnostics knob, see CCR_HINT_Q / CCR_HINT_ITEMS
-  u64 hint_q, hint_items;
+  int lead_every; // progress is published / checked every lead_every tiles (power of two <= lead_tiles)
   // store mode: write fp32 scores instead of selecting (dense score tiles for as_tensor / _argsort).
   // With store_max8 (threshold seeding pre-pass) only the best score of every 8 consecutive items is
   // written: the k-th largest of those group maxima is a lower bound of the k-th largest item score,

@@ -103,19 +103,10 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity, DeviceStatus* st
     }
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, u64* bar, u64 hint) {
-  if (hint)
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint) : "memory");
-  else
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// L2 look-ahead of one box of the tensor map (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, u64* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
 // ---- cta_group::2 (CTA pair) variants ----
 __device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -130,15 +121,10 @@ __device__ __forceinline__ u32 mapa_u32(const void* p, u32 rank) {
   return r;
 }
 // TMA load into OWN shared memory whose bytes are accounted on the LEADER CTA's mbarrier
-__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, int c0, int c1, u32 leader_bar, u64 hint) {
-  if (hint)
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
-  else
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* map, int c0, int c1, u32 leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_commit_2cta(u64* bar) {  // arrives on `bar`'s offset in BOTH CTAs
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -493,21 +479,14 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // together.  A leader that is not slowed down by its own L2 misses (the 6-stage pair
         // pipeline hides them) runs away and every follower then misses too: DRAM reads of 7x the
         // table were measured for CTA pairs at B=4096.  So a producer never leads the slowest peer by
-        // more than lead_tiles.  Peers run concurrently because the grid has at most one CTA per SM;
+        // more than lead_tiles (progress is published and checked every lead_every tiles).  The lead is
+        // chosen by the host so that (splits in flight) x (lead) item tiles stay well inside L2.  Peers
+        // run concurrently because the grid has at most one CTA per SM;
         // should one not be running (shared GPU), the wait gives up after 2 ms and throttling is
         // dropped for the rest of the unit.
         bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
-        const int n_peers = peer_hi - peer_lo, my_peer = unit - peer_lo;
         for (long long t = t0; t < t1; ++t) {
-          if (p.prefetch_tiles > 0) {
-            // L2 look-ahead, one requester per tile and split: the peers take turns
-            const long long tp = t + p.prefetch_tiles;
-            if (tp < t1 && (int)((tp - t0) % n_peers) == my_peer) {
-              for (int kb = 0; kb < num_kb; ++kb)
-                tma_prefetch_2d(&tmap_items, kb * kKBlock, (int)(tp * kITile) + crank * G::kItemRows);
-            }
-          }
-          if (throttle && ((t - t0) & 7) == 0) {
+          if (throttle && ((t - t0) & (long long)(p.lead_every - 1)) == 0) {
             const int mine = (int)(t - t0);
             asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(mine) : "memory");
             unsigned long long w0 = 0;
@@ -533,12 +512,12 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
               if (crank == 0) mbar_expect_tx(&sh->full[stage], 2 * kStageBytes);
               const u32 lbar = mapa_u32(&sh->full[stage], 0);
-              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar, p.hint_q);
-              tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar, p.hint_items);
+              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar);
+              tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar);
             } else {
               mbar_expect_tx(&sh->full[stage], kStageBytes);
-              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage], p.hint_q);
-              tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage], p.hint_items);
+              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
+              tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage]);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

@@ -237,7 +237,8 @@ void ccr_set_profile_events(void* start_event, void* stop_event);
  * bookkeeping.  Fills info8 = { n_q_tiles (units of 128 query rows, or 256 for CTA pairs), n_splits
  * (item splits), cand_capacity (keys per candidate buffer), algo (CCR_ALGO_*), two_cta (0/1),
  * seed_items (sampled items of the threshold-seeding pre-pass, 0 = none), n_kernel_launches (kernels
- * one call launches), prefetch_tiles (L2 look-ahead distance) }.  Returns 0 or CCR_E*. */
+ * one call launches), lead_tiles (bounded drift of the units sharing an item split) }.  Returns 0 or
+ * CCR_E*. */
 int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, int64_t mask_max_row_nnz,
                   int flags, int32_t* info8);
 

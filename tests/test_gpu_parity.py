@@ -131,6 +131,31 @@ def test_ranking_dropin_vs_golden(ccr, name, golden_dir, monkeypatch):
             assert set(got_blocked) <= blocked
 
 
+@pytest.mark.parametrize("name", list(cases.CUDA_RANKING_CASES))
+def test_ranking_dropin_vs_reference_cuda_golden(ccr, name, golden_dir, monkeypatch):
+    """The drop-in against the reference's REAL GPU path: goldens = unmodified ms_marco_eval.ranking on a
+    B200 under torch.cuda.amp.autocast() (fp16 tensor-core scores).  north_star
+    rule: scores within 1e-2 relative, id sets equal up to near-ties at the k-th score."""
+    g = np.load(os.path.join(golden_dir, f"ranking_cuda_autocast_{name}.npz"))
+    c = cases.ranking_case(name)
+    monkeypatch.setenv("CCREC_SIM_TYPE", c["sim_type"])
+    prof = ccr.ranking(c["corpus"], c["queries"], cases.TextTable(c["table"]), c["batch_size"], c["block_dict"])
+    pos = {pid: i for i, pid in enumerate(c["corpus"].keys())}
+    qids = list(c["queries"].keys())
+    assert list(prof.keys()) == qids
+    order = np.array([[pos[p] for p in prof[q].keys()] for q in qids])
+    scores = np.array([list(prof[q].values()) for q in qids])
+    assert order.shape == g["order"].shape
+    live = g["scores"][g["scores"] > -1e6]
+    errs = O.check_topk(scores, order, ref_scores=g["scores"], ref_ids=g["order"], rtol=RTOL,
+                        atol=RTOL * float(np.abs(live).max()))
+    assert not errs, errs[:5]
+    # the pairs the labelling requests are built from (al_0_rank.py:172): same top-2 set in most rows
+    # (fp16 vs bf16 rounding may swap near-ties)
+    same_top2 = np.mean([set(order[b, :2]) == set(g["order"][b, :2]) for b in range(len(qids))])
+    assert same_top2 >= 0.8, same_top2
+
+
 @pytest.mark.parametrize("name", list(cases.RIME_CASES))
 def test_assign_topk_dropin_vs_golden(ccr, name, golden_dir):
     g = np.load(os.path.join(golden_dir, f"rime_{name}.npz"))

@@ -44,6 +44,29 @@ def test_ranking_ref_matches_reference(name, golden_dir):
             assert len(set(order[b])) == order.shape[1]
 
 
+@pytest.mark.parametrize("name", list(cases.CUDA_RANKING_CASES))
+def test_ranking_ref_matches_reference_cuda_autocast_path(name, golden_dir):
+    """the goldens are outputs of the UNMODIFIED ms_marco_eval.ranking run on a
+    B200 with its real .cuda() calls inside torch.cuda.amp.autocast() (al_0_rank.py:125), i.e. fp16
+    tensor-core scores.  The oracle's CPU restatement of that arithmetic must reproduce them up to one
+    fp16 ulp of cuBLAS's accumulation order (and the permutations that such a one-ulp move, or an exact
+    fp16 tie under the reference's unstable sort, allows)."""
+    g = np.load(os.path.join(golden_dir, f"ranking_cuda_autocast_{name}.npz"))
+    c = cases.ranking_case(name)
+    prof = O.ranking_ref(c["corpus"], c["queries"], cases.TextTable(c["table"]), c["batch_size"], c["block_dict"],
+                         sim_type=c["sim_type"], autocast_fp16=True)
+    order, scores = _profile_to_arrays(prof, c)
+    assert order.shape == g["order"].shape
+    live = g["scores"] > -1e6
+    assert np.array_equal(live, scores > -1e6)
+    ulp = np.abs(g["scores"]) * 2.0 ** -10 + 2.0 ** -24      # one fp16 ulp at the score's binade (or coarser)
+    assert (np.abs(scores - g["scores"])[live] <= ulp[live]).all()
+    assert (scores == g["scores"]).mean() > 0.99
+    assert (order == g["order"])[live].mean() > 0.99
+    errs = O.check_topk(scores, order, ref_scores=g["scores"], ref_ids=g["order"], rtol=2.0 ** -9, atol=1e-6)
+    assert not errs, errs[:3]
+
+
 @pytest.mark.parametrize("name", list(cases.RIME_CASES))
 def test_rime_ref_matches_reference(name, golden_dir):
     g = np.load(os.path.join(golden_dir, f"rime_{name}.npz"))
