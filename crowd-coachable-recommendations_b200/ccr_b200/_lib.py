@@ -35,6 +35,9 @@ EXPORTS = [
     "ccr_set_profile_events",
     "ccr_set_status_record",
     "ccr_debug_reload_env",
+    "ccr_argsort_workspace_bytes",
+    "ccr_argsort_scores_f32",
+    "ccr_first_hit_rank",
     "ccr_topk_dense_workspace_bytes",
     "ccr_topk_dense_f32",
     "ccr_bm25_build_impacts",
@@ -95,6 +98,12 @@ def lib():
     L.ccr_set_status_record.argtypes = [vp]
     L.ccr_debug_reload_env.restype = None
     L.ccr_debug_reload_env.argtypes = []
+    L.ccr_argsort_workspace_bytes.restype = sz
+    L.ccr_argsort_workspace_bytes.argtypes = [i64]
+    L.ccr_argsort_scores_f32.restype = i32
+    L.ccr_argsort_scores_f32.argtypes = [vp, i64, i64, i64, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp]
+    L.ccr_first_hit_rank.restype = i32
+    L.ccr_first_hit_rank.argtypes = [vp, i64, i32, vp, vp, vp, vp]
     f64 = c.c_double
     L.ccr_topk_dense_workspace_bytes.restype = sz
     L.ccr_topk_dense_workspace_bytes.argtypes = [i64, i64, i32, i64, i64]

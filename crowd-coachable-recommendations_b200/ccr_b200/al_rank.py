@@ -37,7 +37,15 @@ def mrr_from_profile(qrels, ranking_profile, k_values=(1, 5, 10, 100)):
     results, k_values, metric="mrr")`` -- third party, unvendored and unpinned by the reference;
     its published algorithm: per query the results are ordered by score, the reciprocal rank of the
     first hit with qrels score > 0 inside the top k is summed, the sum is divided by ``len(qrels)``
-    and rounded to 5 digits)."""
+    and rounded to 5 digits).  A ``RankingProfile`` (what ``ccr_b200.ranking`` returns) is scored from
+    its [Q, k] position array by the device first-hit scan; a plain dict takes the per-query loop."""
+    from .ranking import RankingProfile, mrr_at_k
+
+    if isinstance(ranking_profile, RankingProfile) and ranking_profile.order.ndim == 2 and len(ranking_profile):
+        for qid in ranking_profile.queries_ids:
+            qrels[qid]  # BEIR indexes qrels[query_id] for every result: KeyError for an unknown query
+        return mrr_at_k(ranking_profile.order[:, : max(k_values)], ranking_profile.corpus_ids.tolist(),
+                        ranking_profile.queries_ids, qrels, k_values)
     k_max = max(k_values)
     sums = {k: 0.0 for k in k_values}
     for qid, scored in ranking_profile.items():
@@ -70,17 +78,90 @@ def select_candidates(ranks, ranks_bm25, corpus_keys, rng):
     return cands
 
 
+class _Draws:
+    """The reference's ``RandomState(STEP).choice(len(corpus))`` stream, drawn in blocks: a bulk
+    ``randint(0, n, size=m)`` yields exactly the values of m scalar ``choice(n)`` calls (legacy
+    MT19937 stream, checked in tests/test_al_rank_cpu.py), at a fraction of the call overhead."""
+
+    def __init__(self, rng, n, block=4096):
+        self.rng, self.n, self.block = rng, n, block
+        self.buf = np.zeros(0, dtype=np.int64)
+        self.ptr = 0
+
+    def take(self, m):
+        """The next m draws (consumed)."""
+        have = len(self.buf) - self.ptr
+        if have < m:
+            more = self.rng.randint(0, self.n, size=max(self.block, m - have))
+            self.buf = np.concatenate([self.buf[self.ptr:], more])
+            self.ptr = 0
+        out = self.buf[self.ptr : self.ptr + m]
+        self.ptr += m
+        return out
+
+    def give_back(self, m):
+        self.ptr -= m
+
+
+def _fill_fourth(cand_pos, draws):
+    """For queries that hold exactly three candidates (corpus positions [Q, 3]): the fourth is the first
+    draw of the stream that is not one of the three -- queries in order, each consuming draws until one
+    is accepted (al_0_rank.py:178-182).  Vectorised: a run of queries takes one draw each until the
+    first rejection, which is resolved sequentially."""
+    Q = len(cand_pos)
+    fourth = np.empty(Q, dtype=np.int64)
+    i = 0
+    while i < Q:
+        m = Q - i
+        d = draws.take(m)
+        clash = (d[:, None] == cand_pos[i : i + m]).any(axis=1)
+        j = int(np.argmax(clash)) if clash.any() else m
+        fourth[i : i + j] = d[:j]
+        draws.give_back(m - j)          # only j draws were really consumed
+        i += j
+        if j < m:                       # query i rejected its draw: keep drawing for it alone
+            while True:
+                dd = int(draws.take(1)[0])
+                if dd not in cand_pos[i]:
+                    fourth[i] = dd
+                    i += 1
+                    break
+    return fourth
+
+
 def build_requests(ranking_profile, ranking_profile_bm25, corpus, queries, split_qids, step, landing_image=None):
     """-> (header, rows, id_track) for the queries of this step's split, in ranking_profile order."""
     rng = np.random.RandomState(step)
     corpus_keys = list(corpus.keys())
     wanted = split_qids if isinstance(split_qids, (set, frozenset)) else set(np.asarray(split_qids).tolist())
     header = HEADER + (IMAGE_HEADER if landing_image is not None else [])
+    top_ids = getattr(ranking_profile, "top_ids", None)
+    qids = [qid for qid in ranking_profile if qid in wanted]
+    # dense top-2, then the best BM25 passage not among them (al_0_rank.py:169-177)
+    all_cands = []
+    for qid in qids:
+        cands = top_ids(qid, 2) if top_ids is not None else list(ranking_profile[qid].keys())[:2]
+        for pid in ranking_profile_bm25[qid].keys():
+            if len(cands) >= 3:
+                break
+            if pid not in cands:
+                cands.append(pid)
+        all_cands.append(cands)
+    # random corpus passages until there are four distinct ones (:178-182), same draw sequence
+    draws = _Draws(rng, len(corpus_keys))
+    if qids and all(len(c) == 3 for c in all_cands):
+        pos = {pid: i for i, pid in enumerate(corpus_keys)}
+        cand_pos = np.array([[pos[p] for p in c] for c in all_cands], dtype=np.int64)
+        for c, f in zip(all_cands, _fill_fourth(cand_pos, draws)):
+            c.append(corpus_keys[f])
+    else:  # short dense / BM25 lists: some query needs several random picks -> plain sequential loop
+        for c in all_cands:
+            while len(c) < 4:
+                pid = corpus_keys[int(draws.take(1)[0])]
+                if pid not in c:
+                    c.append(pid)
     rows, id_track = [], {}
-    for qid, scored in ranking_profile.items():
-        if qid not in wanted:
-            continue
-        cands = select_candidates(list(scored.keys()), ranking_profile_bm25[qid].keys(), corpus_keys, rng)
+    for qid, cands in zip(qids, all_cands):
         passages = [filter_string(corpus[pid]) for pid in cands]
         row = [queries[qid], *passages, f"q_{qid}", *(f"p_{pid}" for pid in cands)]
         if landing_image is not None:
@@ -171,7 +252,8 @@ def rank_step(corpus, queries, qrels, embedding_func, results_dir, step, ranking
         ranking_profile = torch.load(profile_path)
     else:
         ranking_profile = ranking(corpus, queries, embedding_func, batch_size, block_dict, device=device)
-        torch.save(ranking_profile, profile_path)
+        # the reference's file format is the plain dict (loadable with torch.load's weights-only default)
+        torch.save(ranking_profile.to_dict() if hasattr(ranking_profile, "to_dict") else ranking_profile, profile_path)
     mrr = mrr_from_profile(qrels, ranking_profile, [1, 5, 10, 100])
     for name, value in mrr.items():
         print(name, ":", value)

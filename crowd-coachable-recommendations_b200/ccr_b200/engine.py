@@ -339,6 +339,61 @@ def topk_dense(scores, k, mask: SparseMask | None = None):
     return out_s, out_i, out_d
 
 
+def argsort_scores(scores, mask: SparseMask | None = None):
+    """Whole-matrix argsort of a float32 score matrix [B, N] on the device (+ sparse prior in float64),
+    best first, equal scores in flat order: (rows int64 [B*N], cols int64 [B*N]).  C ABI:
+    ccr_argsort_scores_f32 (LSD radix sort)."""
+    _require_cuda(scores, "scores")
+    if scores.dtype != torch.float32 or scores.dim() != 2 or (scores.shape[1] and scores.stride(1) != 1):
+        raise TypeError("scores must be a 2-d float32 tensor with a contiguous last dimension")
+    B, N = scores.shape
+    dev = scores.device
+    n = B * N
+    ld = scores.stride(0) if B > 1 else max(scores.stride(0), N)
+    if mask is not None and (mask.n_rows != B or mask.n_cols != N):
+        raise ValueError("mask shape does not match the score matrix")
+    nnz = mask.nnz if mask is not None else 0
+    rows = torch.empty(n, dtype=torch.int64, device=dev)
+    cols = torch.empty(n, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        need = L.ccr_argsort_workspace_bytes(n)
+        if need == 0 and n > 0:
+            raise ValueError("argsort: more than 2^31 matrix elements")
+        ws = workspace.get(dev, max(need, 256))
+        rc = L.ccr_argsort_scores_f32(scores.data_ptr(), B, N, ld,
+                                      mask.indptr.data_ptr() if nnz else None, mask.cols.data_ptr() if nnz else None,
+                                      mask.vals.data_ptr() if nnz else None, nnz, mask.mode if nnz else MASK_NONE,
+                                      rows.data_ptr(), cols.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+    _lib.check(rc)
+    return rows, cols
+
+
+def first_hit_rank(ids, rel_indptr, rel_ids):
+    """Per row of ``ids`` [B, k] (ranked, int64, device) the 1-based rank of the first id found in the
+    row's sorted relevant list (CSR: rel_indptr int64 [B+1], rel_ids int64), 0 = none.  C ABI:
+    ccr_first_hit_rank.  Returns int32 [B] on the device."""
+    _require_cuda(ids, "ids")
+    if ids.dtype != torch.int64 or ids.dim() != 2:
+        raise TypeError("ids must be a 2-d int64 tensor")
+    ids = ids.contiguous()
+    B, k = ids.shape
+    dev = ids.device
+    rel_indptr = torch.as_tensor(rel_indptr, dtype=torch.int64).to(dev)
+    rel_ids = torch.as_tensor(rel_ids, dtype=torch.int64).to(dev)
+    if rel_indptr.numel() != B + 1:
+        raise ValueError("rel_indptr must have B + 1 entries")
+    out = torch.empty(B, dtype=torch.int32, device=dev)
+    if B == 0:
+        return out
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ccr_first_hit_rank(ids.data_ptr(), B, k, rel_indptr.data_ptr(),
+                                           rel_ids.data_ptr() if rel_ids.numel() else None, out.data_ptr(),
+                                           _stream_ptr(dev))
+    _lib.check(rc)
+    return out
+
+
 def ingest_rows(src, dst, normalize=False):
     """fp32 (or bf16) rows on the device -> bf16 table rows, optional fp32 L2 normalisation."""
     _require_cuda(src, "src")

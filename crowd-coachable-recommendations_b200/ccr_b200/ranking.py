@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 import os
+from collections.abc import Mapping
 
 import numpy as np
 import torch
@@ -88,6 +89,54 @@ def build_block_mask(queries_ids, corpus_ids, block_dict, device):
     return engine.SparseMask.from_flat(lengths, ind, len(corpus_ids), BLOCK_VALUE, engine.MASK_SET, device)
 
 
+class RankingProfile(Mapping):
+    """The ``{qid: {pid: score}}`` result of ``ranking`` held as the two [Q, k] arrays the kernels
+    produce (scores float32, corpus positions int64).  It behaves like the reference's dict -- keys in
+    query order, ``profile[qid]`` is a dict in descending score order, ``==`` against a dict, pickling
+    yields a plain dict (``rank_step`` saves ``to_dict()`` so ``ranking_profile.pt`` keeps the reference's
+    format and loads under torch.load's weights-only default) --
+    but a row's dict is only built when somebody asks for it (9,862 x 1,001 entries cost 1.2 s up
+    front); MRR and candidate selection read the arrays directly."""
+
+    def __init__(self, queries_ids, corpus_ids, scores, order):
+        self.queries_ids = list(queries_ids)
+        self.corpus_ids = corpus_ids if isinstance(corpus_ids, np.ndarray) else np.asarray(list(corpus_ids), dtype=object)
+        self.scores = np.asarray(scores)
+        self.order = np.asarray(order)
+        self._row_of = {qid: i for i, qid in enumerate(self.queries_ids)}
+        self._cache = {}
+
+    def __getitem__(self, qid):
+        row = self._cache.get(qid)
+        if row is None:
+            i = self._row_of[qid]  # KeyError like a dict
+            row = dict(zip(self.corpus_ids[self.order[i]].tolist(), self.scores[i].tolist()))
+            self._cache[qid] = row
+        return row
+
+    def __iter__(self):
+        return iter(self.queries_ids)
+
+    def __len__(self):
+        return len(self.queries_ids)
+
+    def __contains__(self, qid):
+        return qid in self._row_of
+
+    def top_ids(self, qid, n):
+        """The first ``n`` passage ids of a query without building its dict."""
+        return self.corpus_ids[self.order[self._row_of[qid], :n]].tolist()
+
+    def to_dict(self):
+        return {qid: self[qid] for qid in self.queries_ids}
+
+    def __reduce__(self):
+        return (dict, (self.to_dict(),))
+
+    def __repr__(self):
+        return f"RankingProfile({len(self)} queries x {self.order.shape[1] if self.order.ndim == 2 else 0} passages)"
+
+
 def ranking_tensors(query_table, passage_table, k, mask=None, algo=0):
     """Core of ``ranking``: resident tables -> (scores [Q,k] f32, positions [Q,k] i64) on the host."""
     Q = len(query_table)
@@ -116,28 +165,39 @@ def ranking(corpus, queries, embedding_func, batch_size, block_dict=None, device
         mask = build_block_mask(queries_ids, corpus_ids, block_dict, p_table.device)
     k = min(RANKING_TOPN, len(corpus_ids))
     scores, order = ranking_tensors(q_table, p_table, k, mask, algo=algo)
-    corpus_arr = np.asarray(corpus_ids, dtype=object)
-    ranking_profile = {}
-    for step, qid in enumerate(queries_ids):
-        ranking_profile[qid] = dict(zip(corpus_arr[order[step]].tolist(), scores[step].tolist()))
-    return ranking_profile
+    return RankingProfile(queries_ids, corpus_ids, scores, order)
 
 
-def mrr_at_k(order, corpus_ids, queries_ids, qrels, k_values=(1, 5, 10, 100)):
-    """MRR@k of a ranking produced by ``ranking_tensors`` (positions [Q, k], descending), the
-    metric scripts/al_0_rank.py:130-133 obtains from BEIR's ``evaluate_custom(..., metric="mrr")``:
-    per query the reciprocal rank of the first relevant passage (qrels score > 0) within the top
-    k, averaged over queries, rounded to 5 digits.  Vectorised over queries."""
-    pos = {pid: i for i, pid in enumerate(corpus_ids)}
-    Q, K = order.shape
-    first = np.full(Q, np.inf)
-    for qi, qid in enumerate(queries_ids):
-        rel = [pos[p] for p, s in qrels.get(qid, {}).items() if s > 0 and p in pos]
-        if rel:
-            hit = np.nonzero(np.isin(order[qi], rel))[0]
-            if hit.size:
-                first[qi] = hit[0] + 1
-    return {f"MRR@{k}": round(float(np.mean(np.where(first <= k, 1.0 / first, 0.0))), 5) for k in k_values}
+def qrels_csr(queries_ids, corpus_ids, qrels):
+    """Relevant corpus positions (qrels score > 0) per query as CSR (indptr int64 [Q+1], sorted int64
+    positions); passages outside the corpus are ignored like BEIR ignores unknown doc ids."""
+    pos = corpus_ids if isinstance(corpus_ids, dict) else {pid: i for i, pid in enumerate(corpus_ids)}
+    indptr, rel = [0], []
+    for qid in queries_ids:
+        hits = sorted(pos[p] for p, s in qrels.get(qid, {}).items() if s > 0 and p in pos)
+        rel.extend(hits)
+        indptr.append(len(rel))
+    return np.asarray(indptr, dtype=np.int64), np.asarray(rel, dtype=np.int64)
+
+
+def mrr_at_k(order, corpus_ids, queries_ids, qrels, k_values=(1, 5, 10, 100), device="cuda"):
+    """MRR@k of a ranking given as positions [Q, k] (descending), the metric scripts/al_0_rank.py:130-133
+    obtains from BEIR's ``EvaluateRetrieval.evaluate_custom(qrels, results, k_values, metric="mrr")``
+    (third party, unvendored and unpinned by the reference; its published algorithm): per query the
+    reciprocal rank of the first passage with qrels score > 0 inside the top k is summed, the sum is
+    divided by ``len(qrels)`` and rounded to 5 digits.  The first-hit scan runs on the device
+    (``ccr_first_hit_rank``), one warp per query."""
+    order_t = order if isinstance(order, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(order), dtype=torch.int64)
+    if not order_t.is_cuda:
+        order_t = order_t.to(device)
+    indptr, rel = qrels_csr(queries_ids, corpus_ids, qrels)
+    first = engine.first_hit_rank(order_t, indptr, rel).cpu().numpy().astype(np.float64)
+    n = max(1, len(qrels))
+    out = {}
+    for k in k_values:
+        hit = (first > 0) & (first <= k)
+        out[f"MRR@{k}"] = round(float(np.sum(1.0 / first[hit])) / n, 5)
+    return out
 
 
 def ranking_sharded(corpus, queries, embedding_func, batch_size, block_dict=None, group=None, device=None,
@@ -175,6 +235,4 @@ def ranking_sharded(corpus, queries, embedding_func, batch_size, block_dict=None
         sc, ids, _ = index.search(q_emb[s:e], k, mask=mask.rows(s, e) if mask is not None else None)
         scores[s:e] = sc.cpu().numpy()
         order[s:e] = ids.cpu().numpy()
-    corpus_arr = np.asarray(corpus_ids, dtype=object)
-    return {qid: dict(zip(corpus_arr[order[step]].tolist(), scores[step].tolist()))
-            for step, qid in enumerate(queries_ids)}
+    return RankingProfile(queries_ids, corpus_ids, scores, order)

@@ -281,6 +281,20 @@ class MatMulExpression(_Expression, LazyScoreBase):
         left = type(batch[0].left).collate_fn([b.left for b in batch])
         return MatMulExpression(batch[0].op, [left, batch[0].right])
 
+    def as_tensor(self, device=None):
+        """score_array.py:291-293 of the reference evaluates ``left.as_tensor(device) @
+        right.as_tensor(device)`` with torch.  On a CUDA device a dense x dense product runs through
+        ``ccr_score_dense_f32`` instead (bf16 operands on the cached device table, fp32 accumulate; the
+        TMA + tcgen05 pipeline for tiles of >= 2^20 scores); every other case keeps the generic op."""
+        dev = torch.device(device) if device is not None else None
+        if (dev is not None and dev.type == "cuda" and self.op is operator.matmul
+                and isinstance(self.left, LazyDenseMatrix) and isinstance(self.right, LazyDenseMatrix)):
+            from .util import _device_table_for
+
+            table = _device_table_for(self.right)
+            return table.dense_scores(torch.as_tensor(np.ascontiguousarray(self.left.c)))
+        return super().as_tensor(device)
+
 
 def batch_op_iter(S, op, device=None):
     if isinstance(op, str):

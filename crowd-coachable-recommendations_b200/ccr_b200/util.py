@@ -133,25 +133,29 @@ def _argsort(S, tie_breaker=1e-10, device="cpu"):
     """Drop-in for ``rime_lite.util._argsort`` (src/rime_lite/util/__init__.py:158-184): global flat
     argsort of the whole score matrix, best score first, returned as ``(row_idx, col_idx)``.
 
-    For the hot-path expression shape the dense fp32 scores are produced on the device by
-    ``ccr_score_dense_f32`` (+ the sparse term), then ordered with one device sort (a library
-    radix sort: this sibling API is only used on small reranking sets and is not a hot path,
-    SURVEY.md §8 a11).  Ties are ordered by flat position (the reference adds unseeded jitter)."""
+    The fp32 score matrix is produced on the device (``ccr_score_dense_f32``: the TMA + tcgen05 pipeline
+    with a store epilogue for tiles of >= 2^20 scores) -- or uploaded, when the expression is an already
+    materialised dense matrix -- and ordered by ``ccr_argsort_scores_f32``, an LSD radix sort over
+    float64-ordered keys with the sparse priors merged in float64 like the reference's promotion.
+    Ties are ordered by flat position (the reference adds unseeded jitter)."""
     if not isinstance(S, LazyScoreBase):
         S = auto_cast_lazy_score(S)
     plan = fused_plan(S)
-    if plan is None:
-        raise NotImplementedError(f"_argsort: expression {S!r} is outside the accelerated score-and-rank path")
-    table = _device_table_for(plan.right)
-    dense = table.dense_scores(torch.as_tensor(np.ascontiguousarray(plan.left.c)))
-    if plan.sparse is not None:
-        coo = plan.sparse.tocoo()
-        dense = dense.double()
-        dense.index_put_((torch.as_tensor(coo.row, dtype=torch.int64, device=dense.device),
-                          torch.as_tensor(coo.col, dtype=torch.int64, device=dense.device)),
-                         torch.as_tensor(coo.data, dtype=torch.float64, device=dense.device), accumulate=True)
-    order = torch.sort(dense.reshape(-1), descending=True, stable=True).indices.cpu().numpy()
-    return np.unravel_index(order, plan.shape)
+    if plan is not None:
+        table = _device_table_for(plan.right)
+        dense = table.dense_scores(torch.as_tensor(np.ascontiguousarray(plan.left.c)))
+        sparse = plan.sparse
+    else:
+        dplan = dense_plan(S)
+        if dplan is None or np.asarray(dplan.dense.c).dtype not in (np.float32, np.float16):
+            raise NotImplementedError(f"_argsort: expression {S!r} is outside the accelerated score-and-rank path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("ccr_b200 needs a CUDA device (no CPU path)")
+        dense = torch.as_tensor(np.ascontiguousarray(dplan.dense.c)).to("cuda").float()
+        sparse = dplan.sparse
+    mask = engine.SparseMask.from_scipy(sparse, engine.MASK_ADD, dense.device) if sparse is not None else None
+    rows, cols = engine.argsort_scores(dense, mask)
+    return rows.cpu().numpy(), cols.cpu().numpy()
 
 
 argsort = _argsort

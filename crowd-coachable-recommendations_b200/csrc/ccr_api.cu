@@ -236,20 +236,19 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
 
 // Bounded-drift lead (item tiles) of the units that stream one item split.  The tiles between the
 // slowest and the fastest unit of every split in flight must stay L2-resident or the followers re-read
-// them from HBM: (splits in flight) x lead x tile bytes is held to a budget well inside the 126 MB L2
-// (B=1024 at 8.84M x 768: 18.5 splits in flight x 16 tiles x 393 KB = 116 MB -> 24.6 GB of DRAM reads for
-// a 13.6 GB table, ncu profiles/r02_batch_counters.csv; with the budget: lead 4).
+// them from HBM.  Measured on B200 (profiles/r02_lead_sweep.md, 8.84M x 768): a lead of 16 tiles is the
+// best or within noise everywhere except where many splits are in flight with several units each --
+// B=1024: 18 splits x 16 tiles x 393 KB = 113 MB of window against a 126 MB L2, 24.6 GB of DRAM reads for
+// a 13.6 GB table (ncu, profiles/r02_batch_counters.csv) -- there a lead of 8 is 7 % faster.  Leads of
+// 2-4 tiles stall the producers on the polling itself (every tile) and lose 10-30 %.
 int default_lead_tiles(const Plan& pl, int D, int sms) {
   const int workers = pl.two_cta ? sms / 2 : sms;
   long long conc = (workers + pl.n_q_tiles - 1) / pl.n_q_tiles;
   if (conc > pl.S) conc = pl.S;
   if (conc < 1) conc = 1;
   const long long tile_bytes = (long long)kITile * D * 2;
-  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 32;
-  long long lead = ((long long)mb << 20) / (conc * tile_bytes);
-  if (lead > 16) lead = 16;
-  if (lead < 2) lead = 2;
-  return (int)lead;
+  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 96;
+  return (pl.n_q_tiles >= 4 && conc * 16 * tile_bytes > ((long long)mb << 20)) ? 8 : 16;
 }
 
 int check_shape(long long B, long long n_items, int D, int k, int flags) {
@@ -433,15 +432,16 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   if (lr) return fail(CCR_ECUDA, "select kernel launch failed (%d: %s)", lr, lr > 0 ? cudaGetErrorString((cudaError_t)lr) : "tensor map");
 
   if (has_mask && nnz > 0) {
-    OverrideParams op;
-    op.q = sp.q; op.ldq = sp.ldq; op.B = (int)B;  // sp.q may be the padded staging block (pitch D) op.items = sp.items; op.ldi = ldi; op.n_items = n_items; op.D = D;
+    OverrideParams op = {};
+    // sp.q may be the padded staging block of a short batch: use ITS pitch (sp.ldq), not the caller's
+    op.q = sp.q; op.ldq = sp.ldq; op.B = (int)B; op.items = sp.items; op.ldi = ldi; op.n_items = n_items; op.D = D;
     op.mask_indptr = sp.mask_indptr; op.mask_cols = mask_cols; op.mask_vals = mask_vals; op.nnz = nnz;
     op.mode = mask_mode; op.ovr_hi = (u64*)(ws + pl.off_ovr_hi); op.ovr_lo = (u32*)(ws + pl.off_ovr_lo);
     lr = launch_overrides(op, st);
     if (lr) return fail(CCR_ECUDA, "override kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   }
 
-  FinalizeParams fp;
+  FinalizeParams fp = {};
   fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S * pl.halves; fp.cand = sp.cand; fp.counts = sp.counts;
   fp.g_tau = sp.g_tau;
   fp.drop_cols = (has_mask && nnz > 0 && pl.include_mask) ? mask_cols : nullptr;
@@ -516,9 +516,61 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
   if (B == 0 || n_items == 0) return CCR_OK;
   if (!q || !items || !out) return fail(CCR_EINVAL, "null pointer");
   if (B > 65535) return fail(CCR_EUNSUPPORTED, "dense B > 65535");
+  if (B * n_items >= (1LL << 20) && n_items >= kITile && n_items <= (1LL << 31) - 512 && D <= 4096 &&
+      !(((uintptr_t)q | (uintptr_t)items) & 15)) {
+    // large tiles: the TMA + tcgen05 pipeline of the fused kernel with a store epilogue
+    SelectParams sp = {};
+    sp.q = (const __nv_bfloat16*)q; sp.ldq = ldq; sp.B = (int)B; sp.q_rows = (int)B;
+    sp.items = (const __nv_bfloat16*)items; sp.ldi = ldi; sp.n_items = n_items; sp.D = D;
+    sp.k = 1; sp.k_keep = 1; sp.C = 0;
+    sp.n_q_tiles = (int)((B + kQTile - 1) / kQTile);
+    sp.S = splits_tc(sp.n_q_tiles, (n_items + kITile - 1) / kITile, device_sm_count());
+    sp.status = (DeviceStatus*)g_status_record;
+    sp.dense_out = out; sp.ld_out = ld_out; sp.store_max8 = 0;
+    sp.lead_tiles = 16; sp.lead_every = 8;
+    int lr = launch_select_tc(sp, (cudaStream_t)stream, device_sm_count());
+    if (lr) return fail(CCR_ECUDA, "dense tile launch failed (%d)", lr);
+    return CCR_OK;
+  }
   int lr = launch_dense_f32((const __nv_bfloat16*)q, B, ldq, (const __nv_bfloat16*)items, n_items, ldi, D, out,
                             ld_out, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "dense kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+size_t ccr_argsort_workspace_bytes(int64_t n_elements) {
+  if (n_elements < 0 || n_elements > (1LL << 31)) return 0;
+  return argsort_workspace_bytes(n_elements);
+}
+
+int ccr_argsort_scores_f32(const float* scores, int64_t B, int64_t n_cols, int64_t ld, const int64_t* mask_indptr,
+                           const int32_t* mask_cols, const double* mask_vals, int64_t mask_nnz, int mask_mode,
+                           int64_t* out_rows, int64_t* out_cols, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B < 0 || n_cols < 0 || ld < n_cols) return fail(CCR_EINVAL, "bad argsort shape");
+  if (B * n_cols > (1LL << 31)) return fail(CCR_EUNSUPPORTED, "argsort: more than 2^31 matrix elements");
+  if (mask_mode != CCR_MASK_NONE && mask_mode != CCR_MASK_SET && mask_mode != CCR_MASK_ADD)
+    return fail(CCR_EINVAL, "bad mask_mode %d", mask_mode);
+  if (B * n_cols == 0) return CCR_OK;
+  if (!scores || !out_rows || !out_cols) return fail(CCR_EINVAL, "null pointer");
+  const bool has_mask = mask_mode != CCR_MASK_NONE && mask_indptr != nullptr && mask_nnz > 0;
+  if (has_mask && (!mask_cols || !mask_vals)) return fail(CCR_EINVAL, "mask_cols / mask_vals null");
+  const size_t need = argsort_workspace_bytes(B * n_cols);
+  if (!workspace || workspace_bytes < need) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, need);
+  int lr = launch_argsort(scores, B, n_cols, ld, has_mask ? (const long long*)mask_indptr : nullptr, mask_cols, mask_vals,
+                          has_mask ? mask_nnz : 0, mask_mode, (long long*)out_rows, (long long*)out_cols, workspace,
+                          (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "argsort launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_first_hit_rank(const int64_t* ids, int64_t B, int k, const int64_t* rel_indptr, const int64_t* rel_ids,
+                       int32_t* out_rank, void* stream) {
+  if (B < 0 || k < 1) return fail(CCR_EINVAL, "bad first-hit shape");
+  if (B == 0) return CCR_OK;
+  if (!ids || !rel_indptr || !out_rank) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_first_hit_rank((const long long*)ids, B, k, (const long long*)rel_indptr, (const long long*)rel_ids,
+                                 out_rank, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "first-hit kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
 }
 
@@ -582,7 +634,7 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
                                (u64*)(ws + pl.off_ovr_hi), (u32*)(ws + pl.off_ovr_lo), st);
     if (lr) return fail(CCR_ECUDA, "dense override launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   }
-  FinalizeParams fp;
+  FinalizeParams fp = {};
   fp.B = (int)B; fp.k = k; fp.C = pl.C; fp.S = pl.S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + pl.off_counts);
   fp.g_tau = nullptr;
   fp.drop_cols = has_mask ? mask_cols : nullptr;
@@ -660,7 +712,7 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
   int lr = launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
                             Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
   if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
-  FinalizeParams fp;
+  FinalizeParams fp = {};
   fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
   fp.g_tau = nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
   fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;

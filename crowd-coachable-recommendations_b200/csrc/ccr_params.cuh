@@ -126,6 +126,14 @@ int launch_normalize_bf16(const __nv_bfloat16* src, long long n, int D, long lon
 int launch_dense_f32(const __nv_bfloat16* q, long long B, long long ldq, const __nv_bfloat16* items,
                      long long n, long long ldi, int D, float* out, long long ld_out, cudaStream_t st);
 
+// whole-matrix argsort and MRR first-hit scan (ccr_sort.cu)
+size_t argsort_workspace_bytes(long long n);
+int launch_argsort(const float* scores, long long B, long long N, long long ld, const long long* indptr, const int* cols,
+                   const double* vals, long long nnz, int mode, long long* out_rows, long long* out_cols, void* ws,
+                   cudaStream_t st);
+int launch_first_hit_rank(const long long* ids, long long B, int k, const long long* rel_indptr, const long long* rel_ids,
+                          int* out_rank, cudaStream_t st);
+
 // dense top-k (ccr_kernels.cu)
 constexpr int kDenseSlack = 1024;  // columns one block scans between two prune checks
 int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k, int k_keep,

@@ -390,11 +390,20 @@ static __device__ __noinline__ u64 prune_stream(u64* b, int n, int k, int C, int
   return ((u64)(u32)kept << 32) | (u64)__float_as_uint(new_tau);
 }
 
+// CCR_DEBUG & 512: invariant checks that end in an error record + trap instead of a wild access
+__device__ __forceinline__ void debug_fail(DeviceStatus* st, int where, int extra) {
+  if (st) { st->code = 2; st->where = where; st->block = blockIdx.x; st->extra = extra; }
+  __threadfence_system();
+  __trap();
+}
+
 // Prune every stream of this warp whose buffer could overflow during the next half tile.  Runs
 // after the accumulator has been handed back, i.e. off the MMA critical path.
 __device__ __forceinline__ void prune_pending(SelState& st, const ShareArgs& sh, int k, int C, u32 hist_s,
-                                              u32 stage_s, int debug) {
+                                              u32 stage_s, int debug, DeviceStatus* status) {
   const int lane = threadIdx.x & 31;
+  if ((debug & 512) && (st.cnt > C || st.cnt < 0 || st.k_row > C - 128 || st.k_row < 1))
+    debug_fail(status, 500, st.cnt > C || st.cnt < 0 ? st.cnt : -st.k_row);
   unsigned need = __ballot_sync(0xffffffffu, st.cnt > C - 128);
   while (need) {
     st.n_prune++;
@@ -406,6 +415,7 @@ __device__ __forceinline__ void prune_pending(SelState& st, const ShareArgs& sh,
     const int stream_s = __shfl_sync(0xffffffffu, st.stream, src);
     const int k_s = __shfl_sync(0xffffffffu, st.k_row, src);
     const u64 r = prune_stream(b, n, k_s, C, row_s, stream_s, sh, hist_s, stage_s, debug);
+    if ((debug & 512) && ((int)(r >> 32) > n || (int)(r >> 32) < k_s)) debug_fail(status, 501, (int)(r >> 32));
     if (lane == src) { st.cnt = (int)(r >> 32); st.tau_f = __uint_as_float((u32)r); }
   }
 }
@@ -706,7 +716,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             for (int j = 0; j < 32; ++j) { v[j] = w2[j]; w1[j] = w3[j]; }
           }
         }
-        if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug);
+        if (!(p.debug & 16)) prune_pending(st, sa, k, C, hist_s, stage_s, p.debug, p.status);
         if (!kMask && p.g_hist) {
           // refresh the row bound from the histogram at tiles 4, 8, 16, ... 256 and every 256 after
           const long long ti = t - t0 + 1;

@@ -161,11 +161,37 @@ int ccr_normalize_rows_bf16(const void* src, int64_t n, int D, int64_t ld_src,
 
 /*
  * Dense score tile  out[B, n] = Q . items^T  (fp32) for callers that really want the matrix
- * (LazyScore.as_tensor on small reranking sets: score_array.py:291-293).  CUDA-core kernel,
- * not a hot path.
+ * (LazyScore.as_tensor / _argsort on reranking sets: score_array.py:291-293).  Tiles of at least
+ * 2^20 scores run on the TMA + tcgen05 pipeline of the fused kernel with a store epilogue, smaller
+ * ones on a CUDA-core kernel.
  */
 int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items, int64_t n_items,
                         int64_t ldi, int D, float* out, int64_t ld_out, void* stream);
+
+/*
+ * Whole-matrix argsort: rime_lite `_argsort` (src/rime_lite/util/__init__.py:158-184), which flattens
+ * the evaluated score matrix and sorts ALL of it, best first.  scores [B, ld] float32 on the device
+ * (e.g. written by ccr_score_dense_f32), optional mask CSR as in ccr_topk_dense_f32 (ADD ranks
+ * double(score) + value, SET the value: the reference's float64 promotion).  Output: out_rows /
+ * out_cols int64 [B * n_cols], score descending, equal scores in flat (row-major) order -- the
+ * reference breaks ties with unseeded jitter.  LSD radix sort over ~ord64(double) keys, 8 passes;
+ * B * n_cols <= 2^31.  Workspace from ccr_argsort_workspace_bytes(B * n_cols).
+ */
+size_t ccr_argsort_workspace_bytes(int64_t n_elements);
+int ccr_argsort_scores_f32(const float* scores, int64_t B, int64_t n_cols, int64_t ld, const int64_t* mask_indptr,
+                           const int32_t* mask_cols, const double* mask_vals, int64_t mask_nnz, int mask_mode,
+                           int64_t* out_rows, int64_t* out_cols, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/*
+ * MRR core (scripts/al_0_rank.py:130-133: BEIR evaluate_custom(..., metric="mrr") over the ranking):
+ * per query row the 1-based rank of the first relevant id in its ranked list, 0 if none.
+ *   ids [B, k] int64 ranked best first (as written by ccr_score_topk_bf16; < 0 = padding);
+ *   rel_indptr int64[B+1], rel_ids int64 sorted ascending inside a row (the qrels with score > 0).
+ * MRR@c = sum over rows with 0 < rank <= c of 1 / rank, divided by the number of qrels queries.
+ */
+int ccr_first_hit_rank(const int64_t* ids, int64_t B, int k, const int64_t* rel_indptr, const int64_t* rel_ids,
+                       int32_t* out_rank, void* stream);
 
 /*
  * Top-k of an ALREADY MATERIALISED dense float32 score matrix plus an optional sparse prior: the

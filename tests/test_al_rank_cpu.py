@@ -103,3 +103,48 @@ def test_generate_train_data_matches_reference(name, golden_dir):
         got = al_rank.generate_train_data(qids, qrels, c["ranking_profile"], c["ranking_profile_bm25"], keys, c["step"])
         assert got == want[variant], variant
         assert list(got.keys()) == [q for q in qids if q in want[variant]]
+
+
+def test_block_drawn_candidates_follow_the_scalar_choice_stream():
+    """The vectorised random fill must consume the ``RandomState(STEP).choice(n)`` stream exactly like the
+    reference's one-call-per-attempt loop (al_0_rank.py:178-182): tiny corpora force many rejections."""
+    from ccr_b200 import al_rank
+
+    for n, Q, seed in [(5, 300, 0), (8, 1000, 1), (1500, 700, 2), (9862, 50, 3)]:
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        np.testing.assert_array_equal([a.choice(n) for _ in range(500)], b.randint(0, n, size=500))
+        rs = np.random.RandomState(seed + 10)
+        cand_pos = np.array([rs.choice(n, size=3, replace=False) for _ in range(Q)], dtype=np.int64)
+        want = []
+        ref = np.random.RandomState(seed)
+        for c in cand_pos:
+            while True:
+                d = ref.choice(n)
+                if d not in c:
+                    want.append(d)
+                    break
+        got = al_rank._fill_fourth(cand_pos, al_rank._Draws(np.random.RandomState(seed), n, block=64))
+        np.testing.assert_array_equal(got, want)
+
+
+def test_ranking_profile_behaves_like_the_reference_dict(tmp_path):
+    from ccr_b200.ranking import RankingProfile
+
+    order = np.array([[2, 0, 1], [1, 2, 0]])
+    scores = np.array([[3.0, 2.0, -1e6], [9.0, 8.5, 1.0]], dtype=np.float32)
+    prof = RankingProfile(["q0", "q1"], ["a", "b", "c"], scores, order)
+    plain = {"q0": {"c": 3.0, "a": 2.0, "b": -1e6}, "q1": {"b": 9.0, "c": 8.5, "a": 1.0}}
+    assert list(prof) == ["q0", "q1"] and len(prof) == 2 and "q1" in prof and "zz" not in prof
+    assert list(prof["q0"].items()) == list(plain["q0"].items())      # descending order preserved
+    assert prof == plain and plain == prof and dict(prof.items()) == plain
+    assert prof.top_ids("q1", 2) == ["b", "c"]
+    with pytest.raises(KeyError):
+        prof["zz"]
+    import pickle
+
+    path = tmp_path / "ranking_profile.pt"
+    torch.save(prof.to_dict(), path)                                   # what rank_step writes
+    back = torch.load(path)
+    assert type(back) is dict and back == plain                        # the reference's file format
+    again = pickle.loads(pickle.dumps(prof))                           # generic pickling also yields the dict
+    assert type(again) is dict and again == plain

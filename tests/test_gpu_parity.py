@@ -444,3 +444,85 @@ def test_transform_scores_topk_vs_reference_matrix(ccr, sim):
     got_scores = np.take_along_axis(dense, got, 1)
     errs = O.check_topk(got_scores, got, full_scores=dense, rtol=RTOL, atol=2e-3 if sim == "cos" else 1e-4)
     assert not errs, errs[:3]
+
+
+@pytest.mark.parametrize("B,N,mode", [(7, 300, O.MASK_NONE), (300, 5001, O.MASK_ADD), (64, 40_000, O.MASK_SET),
+                                      (1, 1, O.MASK_NONE), (1500, 7000, O.MASK_ADD)])
+def test_argsort_abi_matches_stable_float64_sort(ccr, B, N, mode):
+    """ccr_argsort_scores_f32 (whole-matrix LSD radix sort; rime_lite _argsort's device core) against a
+    stable descending float64 sort of the same matrix with the priors merged as the reference promotes
+    them; tie-heavy rows included.  Bit-exact (rows, cols)."""
+    from ccr_b200 import engine
+
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(B + N)
+    dense = rs.standard_normal((B, N)).astype(np.float32)
+    dense[::3] = rs.randint(-20, 20, size=dense[::3].shape).astype(np.float32)  # ties, negatives, zeros
+    mask = _mask(rs, B, N, mode, dev, ccr, max_h=min(N, 30)) if mode != O.MASK_NONE else None
+    rows, cols = engine.argsort_scores(torch.as_tensor(dense).to(dev), mask)
+    full = torch.as_tensor(dense).double()
+    if mask is not None:
+        indptr, mc, mv = mask.host
+        for r in range(B):
+            c = torch.as_tensor(mc[indptr[r]:indptr[r + 1]].astype(np.int64))
+            v = torch.as_tensor(mv[indptr[r]:indptr[r + 1]])
+            full[r, c] = v if mode == O.MASK_SET else full[r, c] + v
+    want = torch.sort(full.reshape(-1), descending=True, stable=True).indices.numpy()
+    np.testing.assert_array_equal(rows.cpu().numpy() * N + cols.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,N,D", [(300, 5000, 768), (130, 9001, 200), (1, 1_100_000, 64), (5, 100, 768)])
+def test_dense_score_tile_matches_fp32_product(ccr, B, N, D):
+    """ccr_score_dense_f32: tiles of >= 2^20 scores run on the TMA + tcgen05 pipeline with a store
+    epilogue (ragged last tile, row pitch not a multiple of 4), smaller ones on the CUDA-core kernel;
+    both against torch's fp32 product of the bf16-rounded operands."""
+    dev = torch.device("cuda:0")
+    P = torch.as_tensor(cases.embeddings(N % 97, N, D))
+    Q = torch.as_tensor(cases.embeddings(N % 89, B, D))
+    table = ccr.EmbeddingTable.from_tensor(P, device=dev)
+    got = table.dense_scores(Q)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        want = table.encode_queries(Q).float()[:, :D] @ table.rows.float()[:, :D].T
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert got.shape == (B, N)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=2e-3)
+
+
+def test_lazy_matmul_as_tensor_on_cuda_uses_the_device_kernel(ccr):
+    rs = np.random.RandomState(4)
+    U, V = rs.standard_normal((40, 64)).astype(np.float32), rs.standard_normal((900, 64)).astype(np.float32)
+    S = ccr.LazyDenseMatrix(U) @ ccr.LazyDenseMatrix(V).T
+    got = S.as_tensor("cuda")
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == (40, 900)
+    want = O.bf16_round(torch.as_tensor(U)) @ O.bf16_round(torch.as_tensor(V)).T
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(S.as_tensor("cpu"), torch.as_tensor(U) @ torch.as_tensor(V).T)  # host path unchanged
+
+
+def test_first_hit_rank_and_mrr_denominator(ccr):
+    from ccr_b200 import engine
+
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(5)
+    B, k, N = 500, 100, 5000
+    ids = np.stack([rs.permutation(N)[:k] for _ in range(B)]).astype(np.int64)
+    rel = [np.unique(rs.randint(0, N, size=rs.randint(0, 6))) for _ in range(B)]
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r in rel])]).astype(np.int64)
+    got = engine.first_hit_rank(torch.as_tensor(ids).to(dev), indptr, np.concatenate(rel)).cpu().numpy()
+    want = np.zeros(B, dtype=np.int32)
+    for b in range(B):
+        hit = np.nonzero(np.isin(ids[b], rel[b]))[0]
+        want[b] = hit[0] + 1 if hit.size else 0
+    np.testing.assert_array_equal(got, want)
+    # BEIR divides by len(qrels), not by the number of ranked queries
+    corpus_ids = [f"p{i}" for i in range(N)]
+    qids = [f"q{b}" for b in range(B)]
+    qrels = {q: {corpus_ids[c]: 1 for c in rel[b]} for b, q in enumerate(qids)}
+    qrels["never_ranked"] = {"p0": 1}
+    m = ccr.mrr_at_k(ids, corpus_ids, qids, qrels, k_values=(1, 10, 100))
+    for kk in (1, 10, 100):
+        ok = (want > 0) & (want <= kk)
+        assert m[f"MRR@{kk}"] == round(float(np.sum(1.0 / want[ok])) / (B + 1), 5)
