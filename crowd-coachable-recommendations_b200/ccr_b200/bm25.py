@@ -20,6 +20,7 @@ from .engine import _require_cuda, _stream_ptr, workspace  # noqa: F401
 
 RANKING_TOPN = 1001  # scripts/ms_marco_eval.py:182
 QUERY_CHUNK = 4096   # queries per fused call
+WARP_KERNEL_MAX_TERMS = 32  # libccr_b200: kBmwMaxTerms
 MAX_QUERY_TERMS = 512
 
 
@@ -144,15 +145,36 @@ class BM25(object):
             raise RuntimeError(f"selected index k out of range (k={k} > n={N})")
         for s in range(0, B, QUERY_CHUNK):
             e = min(B, s + QUERY_CHUNK)
-            d_indptr, d_terms, longest = self._device_queries(texts[s:e])
-            with torch.cuda.device(dev):
-                need = L.ccr_bm25_topk_workspace_bytes(e - s, N, k)
-                ws = workspace.get(dev, max(need, 256))
-                rc = L.ccr_bm25_topk(self._indptr.data_ptr(), self._docs.data_ptr(), self._val.data_ptr(),
-                                     d_indptr.data_ptr(), d_terms.data_ptr(), longest, e - s, N, k,
-                                     out_s[s:e].data_ptr(), out_i[s:e].data_ptr(), ws.data_ptr(), ws.numel(),
-                                     _stream_ptr(dev))
-            _lib.check(rc)
+            indptr, terms, _ = self.encode_queries(texts[s:e])
+            lengths = np.diff(indptr)
+            # the library picks its kernel per call from the longest query: the barrier-free warp-private
+            # kernel up to WARP_KERNEL_MAX_TERMS distinct terms, the block-wide one beyond -- so the rare
+            # long queries (whole passages) go in a call of their own and do not slow the short ones down
+            short = np.nonzero(lengths <= WARP_KERNEL_MAX_TERMS)[0]
+            long_ = np.nonzero(lengths > WARP_KERNEL_MAX_TERMS)[0]
+            for rows in (short, long_):
+                if rows.size == 0:
+                    continue
+                whole = rows.size == e - s
+                sub_ptr = indptr if whole else np.concatenate([[0], np.cumsum(lengths[rows])]).astype(np.int64)
+                sub_terms = terms if whole else (np.concatenate([terms[indptr[r]:indptr[r + 1]] for r in rows])
+                                                 if lengths[rows].sum() else np.zeros(0, np.int32))
+                d_indptr = torch.as_tensor(sub_ptr).to(dev)
+                d_terms = torch.as_tensor(sub_terms if sub_terms.size else np.zeros(1, np.int32)).to(dev)
+                n_q = int(rows.size)
+                res_s = out_s[s:e] if whole else torch.empty((n_q, k), dtype=torch.float32, device=dev)
+                res_i = out_i[s:e] if whole else torch.empty((n_q, k), dtype=torch.int64, device=dev)
+                with torch.cuda.device(dev):
+                    need = L.ccr_bm25_topk_workspace_bytes(n_q, N, k)
+                    ws = workspace.get(dev, max(need, 256))
+                    rc = L.ccr_bm25_topk(self._indptr.data_ptr(), self._docs.data_ptr(), self._val.data_ptr(),
+                                         d_indptr.data_ptr(), d_terms.data_ptr(), int(lengths[rows].max()), n_q, N, k,
+                                         res_s.data_ptr(), res_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+                _lib.check(rc)
+                if not whole:
+                    at = torch.as_tensor(rows + s, device=dev)
+                    out_s.index_copy_(0, at, res_s)
+                    out_i.index_copy_(0, at, res_i)
         return out_s, out_i
 
 

@@ -23,6 +23,7 @@ struct Knobs {
   int mask_exclude = 0, two_cta = -1, split_mult = 0, cap_mult = 0, no_share = 0, no_seed = 0, no_hist = 0;
   long long seed_m = 0;
   int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0, l2_budget_mb = 0;
+  int bm25_blockwide = 0;
   float debug_tau = 0.f;
 };
 Knobs g_knobs;
@@ -46,6 +47,7 @@ void load_knobs() {
   k.lead = env_int("CCR_LEAD", 0);
   k.no_qpad = getenv("CCR_NO_QPAD") != nullptr;
   k.l2_budget_mb = env_int("CCR_L2_BUDGET_MB", 0);
+  k.bm25_blockwide = getenv("CCR_BM25_BLOCKWIDE") != nullptr;
   { const char* v = getenv("CCR_DEBUG_TAU"); k.debug_tau = v ? (float)atof(v) : 0.f; }
   g_knobs = k;
 }
@@ -647,19 +649,34 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
 }
 
 // ---- BM25 (lexical sibling of the dense path) ----
-static void bm25_plan(long long Bq, long long N, int k, int* S, int* C, size_t* off_counts, size_t* total) {
+// warp = true: the warp-private kernel (S doc splits per query x kBmwWarps independent streams each);
+// false: the block-wide kernel (queries with more than kBmwMaxTerms distinct terms).  *streams = candidate
+// lists per query handed to finalize.
+static void bm25_plan(long long Bq, long long N, int k, bool warp, int* S, int* C, int* streams, size_t* off_counts,
+                      size_t* total) {
   const int sms = device_sm_count();
   const long long rows = Bq > 0 ? Bq : 1;
-  long long s = ((long long)kBmBlocksPerSm * sms + rows - 1) / rows;  // blocks resident per SM
-  const long long chunks = (N + kBmChunk - 1) / kBmChunk;
-  if (s > chunks) s = chunks;
-  if (s > 1024) s = 1024;  // finalize: kFinMaxStreams
+  long long s, per_block = 1;
+  if (warp) {
+    s = ((long long)kBmwBlocksPerSm * sms + rows - 1) / rows;
+    const long long minis = (N + kBmwMini - 1) / kBmwMini;
+    if (s * kBmwWarps > minis) s = (minis + kBmwWarps - 1) / kBmwWarps;
+    if (s > 1024 / kBmwWarps) s = 1024 / kBmwWarps;  // finalize: kFinMaxStreams
+    per_block = kBmwWarps;
+    *C = cand_capacity(k, kBmwMini);
+  } else {
+    s = ((long long)kBmBlocksPerSm * sms + rows - 1) / rows;  // blocks resident per SM
+    const long long chunks = (N + kBmChunk - 1) / kBmChunk;
+    if (s > chunks) s = chunks;
+    if (s > 1024) s = 1024;  // finalize: kFinMaxStreams
+    *C = cand_capacity(k, kBmSlack);
+  }
   if (s < 1) s = 1;
   *S = (int)s;
-  *C = cand_capacity(k, kBmSlack);
-  const size_t off = align_up((size_t)rows * s * (*C) * sizeof(u64), 256);
+  *streams = (int)(s * per_block);
+  const size_t off = align_up((size_t)rows * (size_t)(*streams) * (*C) * sizeof(u64), 256);
   *off_counts = off;
-  *total = align_up(off + (size_t)rows * s * sizeof(int), 256);
+  *total = align_up(off + (size_t)rows * (size_t)(*streams) * sizeof(int), 256);
 }
 
 int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
@@ -676,9 +693,10 @@ int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs,
 
 size_t ccr_bm25_topk_workspace_bytes(int64_t Bq, int64_t n_docs, int k) {
   if (Bq < 0 || n_docs < 0 || k < 1 || k > CCR_MAX_K) return 0;
-  int S, C; size_t oc, tot;
-  bm25_plan(Bq, n_docs, k, &S, &C, &oc, &tot);
-  return tot;
+  int S, C, ns; size_t oc, tot_w, tot_b;   // the caller does not say how long the queries are: room for either kernel
+  bm25_plan(Bq, n_docs, k, true, &S, &C, &ns, &oc, &tot_w);
+  bm25_plan(Bq, n_docs, k, false, &S, &C, &ns, &oc, &tot_b);
+  return tot_w > tot_b ? tot_w : tot_b;
 }
 
 static int bm25_check(const int64_t* post_indptr, const int64_t* q_indptr, const int32_t* q_terms, int64_t Bq,
@@ -704,16 +722,19 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
   if (k > n_docs) return fail(CCR_EK_RANGE, "selected index k out of range (k=%d > n=%lld)", k, (long long)n_docs);
   if (Bq == 0) return CCR_OK;
   if (!out_scores || !out_ids) return fail(CCR_EINVAL, "null pointer");
-  int S, C; size_t oc, tot;
-  bm25_plan(Bq, n_docs, k, &S, &C, &oc, &tot);
+  const bool warp = max_query_terms <= kBmwMaxTerms && !knobs().bm25_blockwide;
+  int S, C, ns; size_t oc, tot;
+  bm25_plan(Bq, n_docs, k, warp, &S, &C, &ns, &oc, &tot);
   if (!workspace || workspace_bytes < tot) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, tot);
   unsigned char* ws = (unsigned char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
-  int lr = launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
-                            Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
+  int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
+                                        q_terms, Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st)
+                : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
+                                   Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
   if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   FinalizeParams fp = {};
-  fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = S; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
+  fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = ns; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
   fp.g_tau = nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
   fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
@@ -729,10 +750,13 @@ int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, co
   if (ld < n_docs) return fail(CCR_EINVAL, "ld < n_docs");
   if (Bq == 0 || n_docs == 0) return CCR_OK;
   if (!scores) return fail(CCR_EINVAL, "null pointer");
-  int S, C; size_t oc, tot;
-  bm25_plan(Bq, n_docs, 1, &S, &C, &oc, &tot);
-  int lr = launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
-                            Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
+  const bool warp = max_query_terms <= kBmwMaxTerms && !knobs().bm25_blockwide;
+  int S, C, ns; size_t oc, tot;
+  bm25_plan(Bq, n_docs, 1, warp, &S, &C, &ns, &oc, &tot);
+  int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
+                                        q_terms, Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
+                : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
+                                   Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "bm25 scores launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
 }

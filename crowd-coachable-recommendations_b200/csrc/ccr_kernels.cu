@@ -964,6 +964,122 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
 }
 
 // =======================================================================================
+// BM25, warp-private variant (queries of <= kBmwMaxTerms distinct terms -- every realistic query).
+// The block-wide kernel above pays one block barrier per 256 postings.  Here every WARP is an
+// independent worker: it owns a contiguous doc range (1/8 of the block's split), walks it in
+// mini-chunks of 512 docs whose float64 accumulators are private to the warp (4 KB of shared memory),
+// keeps its own per-term cursors, streams 32 postings per step with the next 32 already requested,
+// and ranks into its own candidate buffer -- no block barrier anywhere, only warp votes.  Terms are
+// still applied in q_terms order and a doc has at most one posting per term, so every float64 sum is
+// bit-identical to the block-wide kernel's and to the reference's.
+// =======================================================================================
+__global__ void __launch_bounds__(kBmwWarps * 32) bm25_topk_warp_kernel(
+    const long long* __restrict__ post_indptr, const int* __restrict__ post_docs, const double* __restrict__ post_val,
+    const long long* __restrict__ q_indptr, const int* __restrict__ q_terms, long long N, int k, int C, int S,
+    u64* cand, int* counts, double* dense_out, long long ld_out) {
+  __shared__ double s_acc[kBmwWarps][kBmwMini];
+  __shared__ long long s_cur[kBmwWarps][kBmwMaxTerms];
+  __shared__ long long s_end[kBmwWarps][kBmwMaxTerms];
+  __shared__ int s_nxt[kBmwWarps][kBmwMaxTerms];
+  __shared__ u32 s_hist[kBmwWarps][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long row = blockIdx.y;
+  const int stream = blockIdx.x * kBmwWarps + warp, n_streams = S * kBmwWarps;
+  const long long n_mini = (N + kBmwMini - 1) / kBmwMini;
+  const long long per = (n_mini + n_streams - 1) / n_streams;
+  const long long d0 = (long long)stream * per * kBmwMini;
+  long long d1 = d0 + per * kBmwMini;
+  if (d1 > N) d1 = N;
+  const long long tb = q_indptr[row];
+  const int T = (int)(q_indptr[row + 1] - tb);
+  double* acc = s_acc[warp];
+  long long* cur = s_cur[warp];
+  long long* pend = s_end[warp];
+  int* nxt = s_nxt[warp];
+  u64* buf = cand ? cand + ((long long)row * n_streams + stream) * C : nullptr;
+  if (lane < T && d0 < d1) {  // cursor of term `lane`: first posting with doc >= d0
+    const int term = q_terms[tb + lane];
+    long long lo = post_indptr[term];
+    const long long end = post_indptr[term + 1];
+    long long hi = end;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)post_docs[mid] < d0) lo = mid + 1; else hi = mid; }
+    cur[lane] = lo;
+    pend[lane] = end;
+    nxt[lane] = lo < end ? post_docs[lo] : 0x7fffffff;
+  }
+  __syncwarp();
+  int cnt = 0;             // warp-uniform
+  float tau_f = -INFINITY;
+  u64 tau_key = 0ull;
+  for (long long c0 = d0; c0 < d1; c0 += kBmwMini) {
+    const long long c1 = c0 + kBmwMini < d1 ? c0 + kBmwMini : d1;
+    const int len = (int)(c1 - c0);
+#pragma unroll
+    for (int j = 0; j < kBmwMini / 32; ++j) acc[j * 32 + lane] = 0.0;
+    __syncwarp();
+    for (int t = 0; t < T; ++t) {
+      if ((long long)nxt[t] >= c1) continue;  // warp-uniform: shared-memory value
+      long long e = cur[t];
+      const long long end = pend[t];
+      int doc = e + lane < end ? __ldg(post_docs + e + lane) : 0x7fffffff;
+      double v = e + lane < end ? __ldg(post_val + e + lane) : 0.0;
+      for (;;) {
+        const long long en = e + 32;  // next 32 postings requested before these are applied
+        const int ndoc = en + lane < end ? __ldg(post_docs + en + lane) : 0x7fffffff;
+        const double nv = en + lane < end ? __ldg(post_val + en + lane) : 0.0;
+        const bool in = (long long)doc < c1;  // doc-sorted: the in-range postings are a prefix
+        if (in) acc[doc - (int)c0] += v;
+        const int n_in = __popc(__ballot_sync(0xffffffffu, in));
+        if (n_in < 32) {
+          const int first_out = __shfl_sync(0xffffffffu, doc, n_in);
+          if (lane == 0) { cur[t] = e + n_in; nxt[t] = first_out; }
+          break;
+        }
+        e = en; doc = ndoc; v = nv;
+      }
+      __syncwarp();
+    }
+    __syncwarp();
+    if (dense_out) {
+      double* o = dense_out + row * ld_out + c0;
+      for (int j = lane; j < len; j += 32) o[j] = acc[j];
+    } else {
+      for (int base = 0; base < len; base += 32) {
+        const int j = base + lane;
+        bool pass = false;
+        u64 key = 0ull;
+        if (j < len) {
+          const float sc = (float)acc[j];
+          if (sc >= tau_f) { key = make_key(sc, (u32)(c0 + j)); pass = key > tau_key; }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+        cnt += __popc(m);
+      }
+      __syncwarp();
+      if (cnt > C - kBmwMini) {  // C >= 2k + kBmwMini: room for the next mini-chunk after a prune
+        const u64 pivot = warp_prune(buf, cnt, k, smem_addr(s_hist[warp]), 0u);
+        cnt = k;
+        tau_key = pivot;
+        tau_f = key_score(pivot);
+      }
+    }
+    __syncwarp();
+  }
+  if (counts && lane == 0) counts[(long long)row * n_streams + stream] = cnt;
+}
+
+int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
+                          const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
+                          u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st) {
+  if (Bq <= 0 || N <= 0) return 0;
+  dim3 grid((unsigned)S, (unsigned)Bq);
+  bm25_topk_warp_kernel<<<grid, kBmwWarps * 32, 0, st>>>(post_indptr, post_docs, post_val, q_indptr, q_terms, N, k, C, S,
+                                                        cand, counts, dense_out, ld_out);
+  return (int)cudaGetLastError();
+}
+
+// =======================================================================================
 // Top-k of an already materialised dense float32 score matrix (+ sparse priors): what the
 // reference's `_assign_topk` receives when `BertBPR.transform` hands it the dense host matrix
 // (src/rime_lite/util/__init__.py:135-141 after score_array.py:226-227 [+ :173-174]).

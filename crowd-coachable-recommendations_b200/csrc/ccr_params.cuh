@@ -155,6 +155,14 @@ constexpr int kBmThreads = CCR_BM_THREADS;
 constexpr int kBmBlocksPerSm = CCR_BM_BLOCKS_PER_SM;
 constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query
 constexpr int kBmSlack = 1024;     // accumulators ranked between two prune checks
+// warp-private variant: 8 independent warps per block, 512-doc mini-chunks, <= 32 distinct query terms
+constexpr int kBmwWarps = 8;
+constexpr int kBmwMini = 512;
+constexpr int kBmwMaxTerms = 32;
+constexpr int kBmwBlocksPerSm = 4;   // 45 KB of static shared memory per block
+int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
+                          const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
+                          u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st);
 int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,
                         const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
                         cudaStream_t st);

@@ -73,8 +73,22 @@ def _synthetic(seed, n, q, vocab, doc_len):
     return corpus, queries
 
 
+@pytest.fixture(params=["auto", "blockwide"])
+def bm25_kernel(request):
+    """auto: queries of <= 32 distinct terms take the warp-private kernel, longer ones the block-wide
+    kernel (the batches below hold both kinds); blockwide: everything on the block-wide kernel."""
+    from ccr_b200 import _lib
+
+    if request.param == "blockwide":
+        os.environ["CCR_BM25_BLOCKWIDE"] = "1"
+        _lib.reload_env()
+    yield request.param
+    os.environ.pop("CCR_BM25_BLOCKWIDE", None)
+    _lib.reload_env()
+
+
 @pytest.mark.parametrize("n,q,k", [(40000, 40, 1001), (150000, 300, 100), (9000, 700, 10)])
-def test_bm25_topk_vs_oracle(n, q, k, ccr):
+def test_bm25_topk_vs_oracle(n, q, k, ccr, bm25_kernel):
     corpus, queries = _synthetic(41 + k, n, q, vocab=20000, doc_len=60)
     model = ccr.BM25(b=0.75, k1=1.2).fit(corpus)
     ref = O.BM25Ref(b=0.75, k1=1.2).fit(corpus)
