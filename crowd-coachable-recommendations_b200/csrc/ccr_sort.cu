@@ -84,10 +84,9 @@ __global__ void __launch_bounds__(1024) sort_scan_kernel(u32* __restrict__ hist,
   }
 }
 
-// stable scatter: thread t of warp w owns items [w * 512 + t * 16 ... ) of the tile?  No -- to stay
-// coalesced AND stable, the tile is walked in 16 rounds of 256 consecutive keys; inside a round warp w
-// holds keys [w * 32, w * 32 + 32).  Stable rank of a key = keys of the same digit in earlier rounds
-// + in earlier warps of this round + in lower lanes of its warp.
+// Stable scatter.  To stay coalesced AND stable the tile is walked in 16 rounds of 256 consecutive keys;
+// inside a round warp w holds keys [32 w, 32 w + 32).  Stable rank of a key = keys of the same digit in
+// earlier rounds (accumulated into s_base) + in earlier warps of this round + in lower lanes of its warp.
 __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(const u64* __restrict__ keys_in,
                                                                     const u32* __restrict__ pay_in, long long n,
                                                                     int shift, const u32* __restrict__ hist,

@@ -22,6 +22,8 @@ def test_sharded_search_matches_oracle(world):
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-4000:]
+    # dist_check.py exits non-zero if ANY rank saw a mismatch (all-reduce MIN of the per-rank verdicts)
     assert r.returncode == 0, tail
-    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("rank ")]
-    assert len(lines) >= 7 * world and all("equal_single_table=True oracle_violations=0" in ln for ln in lines), tail
+    # ranks share stdout, so their report lines may interleave: count the verdict tokens, not the lines
+    assert r.stdout.count("equal_single_table=True oracle_violations=0") == 7 * world, tail
+    assert "equal_single_table=False" not in r.stdout, tail
