@@ -12,8 +12,9 @@ score(Q . P^T) -> history mask (set -1e6) -> per-row top-k.
 --config c5 (BASELINE.json configs[4]): 100,000,000 x 768 bf16 row-sharded over the ranks (19.2 GB each at
     8 GPUs; needs >= 8 GPUs of 180 GB -- or 1 GPU for a single 12.5 M-row shard with --n-items), top-1000.
 
-With N > 1 every rank computes its local top-k, ONE all-gather of packed 8-byte (float32 score, uint32
-global id) keys is followed by an on-device G-way merge-path merge.
+With N > 1 every rank computes its local top-k as packed 8-byte (float32 score, uint32 global id) keys; an
+all-to-all hands every rank the runs of its B/G query rows, an on-device G-way merge-path merge and an
+all-gather of the merged rows complete the result on every rank.
 
 value  : queries/s, whole job, inputs (bf16 table shard, bf16 queries, mask CSR) resident in HBM.
 e2e    : the same through the public host API from HOST buffers: pinned fp32 queries (each rank uploads
@@ -325,10 +326,7 @@ def run_ours(args):
 
     def step_resident():
         if world > 1:
-            keys = index._local_topk_keys(q_dev, k, mask_local)
-            gk = torch.empty((world * B, k), dtype=keys.dtype, device=dev)
-            dist.all_gather_into_tensor(gk, keys)
-            return engine.merge_topk_keys(gk.view(world, B, k), k)
+            return index._exchange_keys(index._local_topk_keys(q_dev, k, mask_local), k)
         return table.search(q_dev, k, mask=mask_local, encoded=True)
 
     def step_e2e():
@@ -397,7 +395,7 @@ def run_ours(args):
     hbm_bytes = float(n_local) * DIM * 2        # algorithmic bytes: the shard once
     t_tensor, t_hbm = flops / (pk["tflops_burst"] * 1e12), hbm_bytes / (pk["hbm"] * 1e9)
     plan = _lib.plan_info(B, n_local, DIM, k, mask_nnz=int(indptr[-1]), mask_max_row_nnz=mask_global.max_row_nnz)
-    launches_per_step = plan["n_kernel_launches"] + (1 if world > 1 else 0)   # + G-way merge; NCCL kernels not counted
+    launches_per_step = plan["n_kernel_launches"] + (2 if world > 1 else 0)   # + merge + key unpack; NCCL kernels not counted
     # which cuBLAS peak the kernel is compared with: the sustained (power-capped) figure when the sampled
     # clock shows the cap at work, the burst figure when the GPU ran un-capped
     capped = "sw_power_cap" in clocks.get("reasons", []) or (clocks.get("sm_mhz") or 0) < 1600

@@ -26,6 +26,7 @@ EXPORTS = [
     "ccr_score_topk_workspace_bytes",
     "ccr_merge_topk",
     "ccr_merge_topk_keys",
+    "ccr_unpack_topk_keys",
     "ccr_mask_column_shard",
     "ccr_ingest_rows_f32",
     "ccr_normalize_rows_bf16",
@@ -79,7 +80,9 @@ def lib():
     L.ccr_merge_topk.restype = i32
     L.ccr_merge_topk.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, vp, vp]
     L.ccr_merge_topk_keys.restype = i32
-    L.ccr_merge_topk_keys.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp]
+    L.ccr_merge_topk_keys.argtypes = [vp, i32, i64, i32, i32, vp, vp, vp, vp]
+    L.ccr_unpack_topk_keys.restype = i32
+    L.ccr_unpack_topk_keys.argtypes = [vp, i64, vp, vp, vp]
     L.ccr_mask_column_shard.restype = i32
     L.ccr_mask_column_shard.argtypes = [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp]
     L.ccr_ingest_rows_f32.restype = i32

@@ -1,6 +1,8 @@
 """Row-sharded item table across the GPUs of one box: one process per GPU, local fused
-top-k with global ids, ONE all-gather of packed 8-byte (float32 score, uint32 id) keys -- or, when
-float64 priors decide the order, of (float64 score, int64 id) pairs -- and an on-device G-way merge.  The reference has no counterpart (it scores on GPU 0 only, scripts/ms_marco_eval.py:205).
+top-k with global ids, then the exchange: packed 8-byte (float32 score, uint32 id) keys go through an
+all-to-all (every rank receives all runs of its B/G query rows), an on-device G-way merge-path merge
+and an all-gather of the merged rows -- or, when float64 priors decide the order, one all-gather of
+(float64 score, int64 id) pairs and the merge of all rows on every rank.  The reference has no counterpart (it scores on GPU 0 only, scripts/ms_marco_eval.py:205).
 """
 from __future__ import annotations
 
@@ -46,8 +48,28 @@ class ShardedIndex:
     def _merge(self, scores64, ids, k):
         return engine.merge_topk(scores64, ids, k)
 
-    def _merge_keys(self, keys, k):
-        return engine.merge_topk_keys(keys, k)
+    def _merge_keys(self, keys, k, packed=False):
+        return engine.merge_topk_keys(keys, k, packed=packed)
+
+    def _unpack_keys(self, keys):
+        return engine.unpack_topk_keys(keys)
+
+    def _exchange_keys(self, keys, k):
+        """Local sorted runs [B, k] of packed keys on every rank -> global top-k (scores, ids) on every
+        rank.  Query-sharded: an all-to-all hands rank r every rank's runs of ITS slice of the queries
+        (B/G rows), it merges only those, and an all-gather of the merged, still packed rows completes
+        the result: 2 B k 8 bytes cross each link per rank instead of G B k 8, and every rank merges
+        B/G rows instead of B."""
+        G, B = self.world, keys.shape[0]
+        per = (B + G - 1) // G
+        if per * G != B:
+            keys = torch.cat([keys, keys.new_zeros((per * G - B, k))])  # key 0 = padding
+        recv = torch.empty_like(keys)                       # [G, per, k]: block g = rank g's runs of my rows
+        dist.all_to_all_single(recv, keys.contiguous(), group=self.group)
+        mine = self._merge_keys(recv.view(G, per, k), k, packed=True)
+        full = torch.empty((G * per, k), dtype=keys.dtype, device=keys.device)
+        dist.all_gather_into_tensor(full, mine.contiguous(), group=self.group)
+        return self._unpack_keys(full[:B])
 
     def _encode(self, queries):
         return self.table.encode_queries(queries)
@@ -102,10 +124,7 @@ class ShardedIndex:
             keys = self._local_topk_keys(q, k, local_mask)
             if self.world == 1:
                 return (*self._merge_keys(keys.unsqueeze(0), k), None)
-            B = keys.shape[0]
-            gk = torch.empty((self.world * B, k), dtype=keys.dtype, device=keys.device)   # rank-major
-            dist.all_gather_into_tensor(gk, keys.contiguous(), group=self.group)
-            return (*self._merge_keys(gk.view(self.world, B, k), k), None)
+            return (*self._exchange_keys(keys, k), None)
         d, i = self._local_topk(q, k, local_mask)
         if self.world == 1:
             return self._merge(d.unsqueeze(0), i.unsqueeze(0), k)

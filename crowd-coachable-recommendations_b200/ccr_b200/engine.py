@@ -293,18 +293,40 @@ def merge_topk(scores64, ids, k_out):
     return out_s, out_i, out_d
 
 
-def merge_topk_keys(keys, k_out):
-    """[G,B,k_in] packed exchange keys (int64 bit patterns) -> merged (scores f32, ids i64) [B,k_out]
-    (C ABI: ccr_merge_topk_keys)."""
+def merge_topk_keys(keys, k_out, packed=False):
+    """[G,B,k_in] packed exchange keys (int64 bit patterns) -> merged (scores f32, ids i64) [B,k_out], or
+    with ``packed`` the merged runs still as keys [B,k_out] (C ABI: ccr_merge_topk_keys)."""
     _require_cuda(keys, "keys")
     G, B, k_in = keys.shape
     keys = keys.contiguous()
     dev = keys.device
+    if packed:
+        out_k = torch.empty((B, k_out), dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().ccr_merge_topk_keys(keys.data_ptr(), G, B, k_in, k_out, None, None, out_k.data_ptr(),
+                                                _stream_ptr(dev))
+        _lib.check(rc)
+        return out_k
     out_s = torch.empty((B, k_out), dtype=torch.float32, device=dev)
     out_i = torch.empty((B, k_out), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
-        rc = _lib.lib().ccr_merge_topk_keys(keys.data_ptr(), G, B, k_in, k_out, out_s.data_ptr(), out_i.data_ptr(),
+        rc = _lib.lib().ccr_merge_topk_keys(keys.data_ptr(), G, B, k_in, k_out, out_s.data_ptr(), out_i.data_ptr(), None,
                                             _stream_ptr(dev))
+    _lib.check(rc)
+    return out_s, out_i
+
+
+def unpack_topk_keys(keys):
+    """Packed exchange keys (any shape, int64 bit patterns) -> (scores f32, ids i64) of the same shape
+    (C ABI: ccr_unpack_topk_keys)."""
+    _require_cuda(keys, "keys")
+    keys = keys.contiguous()
+    dev = keys.device
+    out_s = torch.empty(keys.shape, dtype=torch.float32, device=dev)
+    out_i = torch.empty(keys.shape, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().ccr_unpack_topk_keys(keys.data_ptr(), keys.numel(), out_s.data_ptr(), out_i.data_ptr(),
+                                             _stream_ptr(dev))
     _lib.check(rc)
     return out_s, out_i
 

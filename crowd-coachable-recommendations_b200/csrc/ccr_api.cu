@@ -470,13 +470,23 @@ int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B,
 }
 
 int ccr_merge_topk_keys(const uint64_t* keys, int G, int64_t B, int k_in, int k_out, float* out_scores,
-                        int64_t* out_ids, void* stream) {
+                        int64_t* out_ids, uint64_t* out_keys, void* stream) {
   if (G < 1 || B < 0 || k_in < 1 || k_out < 1) return fail(CCR_EINVAL, "bad merge shape G=%d B=%lld k_in=%d k_out=%d", G, (long long)B, k_in, k_out);
   if (B == 0) return CCR_OK;
-  if (!keys || !out_ids) return fail(CCR_EINVAL, "null pointer");
-  int lr = launch_merge_keys((const u64*)keys, G, B, k_in, k_out, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+  if (!keys || (!out_ids && !out_keys)) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_merge_keys((const u64*)keys, G, B, k_in, k_out, out_scores, (long long*)out_ids, (u64*)out_keys,
+                             (cudaStream_t)stream);
   if (lr == (int)cudaErrorInvalidValue) return fail(CCR_EUNSUPPORTED, "merge: G * k_in = %lld keys do not fit shared memory", (long long)G * k_in);
   if (lr) return fail(CCR_ECUDA, "key merge kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
+int ccr_unpack_topk_keys(const uint64_t* keys, int64_t n, float* out_scores, int64_t* out_ids, void* stream) {
+  if (n < 0) return fail(CCR_EINVAL, "bad key count");
+  if (n == 0) return CCR_OK;
+  if (!keys) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_unpack_keys((const u64*)keys, n, out_scores, (long long*)out_ids, (cudaStream_t)stream);
+  if (lr) return fail(CCR_ECUDA, "key unpack kernel launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
 }
 

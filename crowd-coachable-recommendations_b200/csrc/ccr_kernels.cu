@@ -550,7 +550,7 @@ int launch_merge_topk(const double* s, const long long* ids, int G, long long B,
 constexpr int kMergeSeg = 4;
 
 __global__ void __launch_bounds__(1024) merge_keys_kernel(const u64* __restrict__ keys, int G, long long B, int k_in,
-                                                          int k_out, int n0, float* os, long long* oi) {
+                                                          int k_out, int n0, float* os, long long* oi, u64* ok) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* buf0 = reinterpret_cast<u64*>(merge_smem);   // n0 keys: the G input runs, later the even rounds' outputs
   u64* buf1 = buf0 + n0;                            // the odd rounds' outputs
@@ -600,12 +600,13 @@ __global__ void __launch_bounds__(1024) merge_keys_kernel(const u64* __restrict_
   for (int r = threadIdx.x; r < k_out; r += blockDim.x) {
     const u64 key = r < len ? src[r] : 0ull;
     const long long o = row * k_out + r;
-    if (key) { if (os) os[o] = key_score(key); oi[o] = (long long)key_id(key); }
-    else { if (os) os[o] = -INFINITY; oi[o] = -1; }
+    if (ok) ok[o] = key;
+    if (key) { if (os) os[o] = key_score(key); if (oi) oi[o] = (long long)key_id(key); }
+    else { if (os) os[o] = -INFINITY; if (oi) oi[o] = -1; }
   }
 }
 
-int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi,
+int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi, u64* ok,
                       cudaStream_t st) {
   if (B == 0) return 0;
   const int ol = 2 * k_in < k_out ? 2 * k_in : k_out;
@@ -636,7 +637,23 @@ int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, 
   int threads = (int)(((size_t)(G / 2) * ((ol + kMergeSeg - 1) / kMergeSeg) + 31) / 32 * 32);
   if (threads < 128) threads = 128;
   if (threads > 1024) threads = 1024;
-  merge_keys_kernel<<<(unsigned)B, threads, smem, st>>>(keys, G, B, k_in, k_out, (int)n0, os, oi);
+  merge_keys_kernel<<<(unsigned)B, threads, smem, st>>>(keys, G, B, k_in, k_out, (int)n0, os, oi, ok);
+  return (int)cudaGetLastError();
+}
+
+// packed exchange keys -> (float32 score, int64 global id); key 0 = padding -> (-inf, -1)
+__global__ void __launch_bounds__(256) unpack_keys_kernel(const u64* __restrict__ keys, long long n, float* os,
+                                                          long long* oi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 key = keys[i];
+  if (os) os[i] = key ? key_score(key) : -INFINITY;
+  if (oi) oi[i] = key ? (long long)key_id(key) : -1;
+}
+
+int launch_unpack_keys(const u64* keys, long long n, float* os, long long* oi, cudaStream_t st) {
+  if (n <= 0) return 0;
+  unpack_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, os, oi);
   return (int)cudaGetLastError();
 }
 
@@ -968,12 +985,12 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
 // The block-wide kernel above pays one block barrier per 256 postings.  Here every WARP is an
 // independent worker: it owns a contiguous doc range (1/8 of the block's split), walks it in
 // mini-chunks of 512 docs whose float64 accumulators are private to the warp (4 KB of shared memory),
-// keeps its own per-term cursors, streams 32 postings per step with the next 32 already requested,
-// and ranks into its own candidate buffer -- no block barrier anywhere, only warp votes.  Terms are
+// keeps its own per-term cursors, streams 32 postings per step (a ring of 4 x 32 in flight once a term
+// turns out to be dense in the mini-chunk), and ranks into its own candidate buffer -- no block barrier anywhere, only warp votes.  Terms are
 // still applied in q_terms order and a doc has at most one posting per term, so every float64 sum is
 // bit-identical to the block-wide kernel's and to the reference's.
 // =======================================================================================
-__global__ void __launch_bounds__(kBmwWarps * 32) bm25_topk_warp_kernel(
+__global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_warp_kernel(
     const long long* __restrict__ post_indptr, const int* __restrict__ post_docs, const double* __restrict__ post_val,
     const long long* __restrict__ q_indptr, const int* __restrict__ q_terms, long long N, int k, int C, int S,
     u64* cand, int* counts, double* dense_out, long long ld_out) {
@@ -1021,21 +1038,51 @@ __global__ void __launch_bounds__(kBmwWarps * 32) bm25_topk_warp_kernel(
       if ((long long)nxt[t] >= c1) continue;  // warp-uniform: shared-memory value
       long long e = cur[t];
       const long long end = pend[t];
-      int doc = e + lane < end ? __ldg(post_docs + e + lane) : 0x7fffffff;
-      double v = e + lane < end ? __ldg(post_val + e + lane) : 0.0;
-      for (;;) {
-        const long long en = e + 32;  // next 32 postings requested before these are applied
-        const int ndoc = en + lane < end ? __ldg(post_docs + en + lane) : 0x7fffffff;
-        const double nv = en + lane < end ? __ldg(post_val + en + lane) : 0.0;
+      bool more = true;
+      {  // first 32 postings on their own: most (term, mini-chunk) visits end inside them
+        const int doc = e + lane < end ? __ldg(post_docs + e + lane) : 0x7fffffff;
+        const double v = e + lane < end ? __ldg(post_val + e + lane) : 0.0;
         const bool in = (long long)doc < c1;  // doc-sorted: the in-range postings are a prefix
         if (in) acc[doc - (int)c0] += v;
         const int n_in = __popc(__ballot_sync(0xffffffffu, in));
         if (n_in < 32) {
           const int first_out = __shfl_sync(0xffffffffu, doc, n_in);
           if (lane == 0) { cur[t] = e + n_in; nxt[t] = first_out; }
-          break;
+          more = false;
         }
-        e = en; doc = ndoc; v = nv;
+        e += 32;
+      }
+      if (more) {
+        // dense term: a ring of kBmwDepth x 32 postings in flight per warp; a slot is refilled as soon
+        // as it has been applied (speculative beyond the range: harmless, guarded by `end`)
+        int doc[kBmwDepth];
+        double v[kBmwDepth];
+#pragma unroll
+        for (int u = 0; u < kBmwDepth; ++u) {
+          const long long i = e + u * 32 + lane;
+          doc[u] = i < end ? __ldg(post_docs + i) : 0x7fffffff;
+          v[u] = i < end ? __ldg(post_val + i) : 0.0;
+        }
+        while (more) {
+#pragma unroll
+          for (int u = 0; u < kBmwDepth; ++u) {
+            if (more) {  // warp-uniform
+              const bool in = (long long)doc[u] < c1;
+              if (in) acc[doc[u] - (int)c0] += v[u];
+              const int n_in = __popc(__ballot_sync(0xffffffffu, in));
+              if (n_in < 32) {
+                const int first_out = __shfl_sync(0xffffffffu, doc[u], n_in);
+                if (lane == 0) { cur[t] = e + u * 32 + n_in; nxt[t] = first_out; }
+                more = false;
+              } else {
+                const long long i = e + (u + kBmwDepth) * 32 + lane;
+                doc[u] = i < end ? __ldg(post_docs + i) : 0x7fffffff;
+                v[u] = i < end ? __ldg(post_val + i) : 0.0;
+              }
+            }
+          }
+          e += kBmwDepth * 32;
+        }
       }
       __syncwarp();
     }

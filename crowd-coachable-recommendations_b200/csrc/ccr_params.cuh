@@ -115,8 +115,9 @@ int launch_overrides(const OverrideParams& p, cudaStream_t st);
 int launch_finalize(const FinalizeParams& p, cudaStream_t st);
 int launch_merge_topk(const double* s, const long long* ids, int G, long long B, int k_in, int k_out,
                       float* os, double* os64, long long* oi, cudaStream_t st);
-int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi,
+int launch_merge_keys(const u64* keys, int G, long long B, int k_in, int k_out, float* os, long long* oi, u64* ok,
                       cudaStream_t st);
+int launch_unpack_keys(const u64* keys, long long n, float* os, long long* oi, cudaStream_t st);
 int launch_mask_shard(const long long* indptr, const int* cols, const double* vals, long long B, int lo, int hi,
                       long long* out_indptr, int* out_cols, double* out_vals, cudaStream_t st);
 int launch_ingest_f32(const float* src, long long n, int D, long long ld_src, __nv_bfloat16* dst,
@@ -155,11 +156,12 @@ constexpr int kBmThreads = CCR_BM_THREADS;
 constexpr int kBmBlocksPerSm = CCR_BM_BLOCKS_PER_SM;
 constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query
 constexpr int kBmSlack = 1024;     // accumulators ranked between two prune checks
-// warp-private variant: 8 independent warps per block, 512-doc mini-chunks, <= 32 distinct query terms
+// warp-private variant: 8 independent warps per block, 512-doc mini-chunks, <= 16 distinct query terms
 constexpr int kBmwWarps = 8;
 constexpr int kBmwMini = 512;
-constexpr int kBmwMaxTerms = 32;
-constexpr int kBmwBlocksPerSm = 4;   // 45 KB of static shared memory per block
+constexpr int kBmwMaxTerms = 16;
+constexpr int kBmwDepth = 4;         // batches of 32 postings in flight per warp on a dense term
+constexpr int kBmwBlocksPerSm = 5;   // 42.5 KB of static shared memory per block
 int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
                           const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
                           u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st);

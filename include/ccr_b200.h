@@ -127,14 +127,16 @@ int ccr_merge_topk(const double* scores64, const int64_t* ids, int G, int64_t B,
 
 /*
  * The same merge for runs in the packed exchange format of CCR_FLAG_PACKED_KEYS:
- *   keys [G, B, k_in] uint64, each run sorted descending (0 = padding).  Output: out_scores
- *   float32 [B, k_out] (may be NULL), out_ids int64 [B, k_out] (global ids; -1 / -inf padding).
- * One all-gather of 8 bytes per entry instead of two of 8; merge-path
- * merges in shared memory.  G * k_in keys must fit shared memory (CCR_EUNSUPPORTED otherwise:
- * G * k_in <= ~16 K).
+ *   keys [G, B, k_in] uint64, each run sorted descending (0 = padding).  Outputs (each may be NULL, not
+ *   both of out_ids / out_keys): out_scores float32 [B, k_out], out_ids int64 [B, k_out] (global ids;
+ *   -1 / -inf padding), out_keys uint64 [B, k_out] the merged run still packed (for a further exchange).
+ * 8 bytes per entry on the wire instead of 16; merge-path merges in shared
+ * memory.  G * k_in keys must fit shared memory (CCR_EUNSUPPORTED otherwise: G * k_in <= ~16 K).
+ * ccr_unpack_topk_keys turns n packed keys into (float32 score, int64 id) pairs.
  */
 int ccr_merge_topk_keys(const uint64_t* keys, int G, int64_t B, int k_in, int k_out, float* out_scores,
-                        int64_t* out_ids, void* stream);
+                        int64_t* out_ids, uint64_t* out_keys, void* stream);
+int ccr_unpack_topk_keys(const uint64_t* keys, int64_t n, float* out_scores, int64_t* out_ids, void* stream);
 
 /*
  * Column shard of a device mask CSR for a row-sharded table: entries with col_lo <= col < col_hi,

@@ -152,10 +152,16 @@ def _worker_ranking(rank, world, port, ret):
             CpuIndex.packed_calls += 1
             return torch.as_tensor(keys.view(np.int64))
 
-        def _merge_keys(self, keys, kk):
+        def _merge_keys(self, keys, kk, packed=False):
             G, Bq, kin = keys.shape
             flat = np.ascontiguousarray(keys.permute(1, 0, 2).reshape(Bq, G * kin).numpy()).view(np.uint64)
             top = np.ascontiguousarray(np.sort(flat, axis=1)[:, ::-1][:, :kk])  # descending
+            if packed:
+                return torch.as_tensor(top.view(np.int64))
+            return self._unpack_keys(torch.as_tensor(top.view(np.int64)))
+
+        def _unpack_keys(self, keys):
+            top = np.ascontiguousarray(keys.numpy()).view(np.uint64)
             o = (top >> np.uint64(32)).astype(np.uint32)
             f = np.where(o >> 31, o & 0x7FFFFFFF, ~o).astype(np.uint32).view(np.float32)
             ids = (np.uint64(0xFFFFFFFF) - (top & np.uint64(0xFFFFFFFF))).astype(np.int64)

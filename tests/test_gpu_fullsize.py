@@ -95,8 +95,8 @@ def test_bench_workload_every_row_vs_fp32_oracle(ccr, bench, big):
     rows_of = np.repeat(np.arange(B), np.diff(indptr))
     hit = (i.cpu().numpy()[rows_of] == cols[:, None].astype(np.int64)).any()
     assert not hit
-    # the L2 look-ahead, the single-CTA variant and histogram sharing change scheduling only: same bits
-    for env in ({"CCR_PREFETCH": "6"}, {"CCR_2CTA": "0"}, {"CCR_NO_HIST": "1"}):
+    # the throttle lead, the single-CTA variant and histogram sharing change scheduling only: same bits
+    for env in ({"CCR_LEAD": "4"}, {"CCR_2CTA": "0"}, {"CCR_NO_HIST": "1"}):
         os.environ.update(env)
         _lib.reload_env()
         try:
@@ -141,6 +141,12 @@ def test_c5_shard_k1000_global_ids_and_packed_keys(ccr, bench, big):
     ms, mi = ccr.merge_topk_keys(runs, k)
     flat = np.sort(runs.cpu().numpy().view(np.uint64).transpose(1, 0, 2).reshape(B, -1), axis=1)[:, ::-1][:, :k]
     np.testing.assert_array_equal(mi.cpu().numpy(), 0xFFFFFFFF - (flat & np.uint64(0xFFFFFFFF)).astype(np.int64))
+    mk = ccr.merge_topk_keys(runs, k, packed=True)                       # still packed, for a further exchange
+    np.testing.assert_array_equal(mk.cpu().numpy().view(np.uint64), flat)
+    us, ui = ccr.engine.unpack_topk_keys(mk)
+    assert torch.equal(us, ms) and torch.equal(ui, mi)
+    us0, ui0 = ccr.engine.unpack_topk_keys(torch.zeros(3, 5, dtype=torch.int64, device=mk.device))
+    assert bool((ui0 == -1).all()) and bool(torch.isinf(us0).all())      # key 0 = padding
 
 
 @pytest.mark.parametrize("B", [1, 128, 512, 1024])
