@@ -668,6 +668,9 @@ static void bm25_plan(long long Bq, long long N, int k, bool warp, int* S, int* 
   const long long rows = Bq > 0 ? Bq : 1;
   long long s, per_block = 1;
   if (warp) {
+    // one resident set of blocks; finer doc splits were measured slower (more streams for finalize to
+    // merge and more cursor searches than the better balance across Zipf queries buys: 42.9 ms at 1x,
+    // 49.0 at 8x, 92.8 at 32x, profiles/r02_bm25.md)
     s = ((long long)kBmwBlocksPerSm * sms + rows - 1) / rows;
     const long long minis = (N + kBmwMini - 1) / kBmwMini;
     if (s * kBmwWarps > minis) s = (minis + kBmwWarps - 1) / kBmwWarps;
