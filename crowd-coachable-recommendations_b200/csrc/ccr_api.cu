@@ -689,7 +689,8 @@ static void bm25_plan(long long Bq, long long N, int k, bool warp, int* S, int* 
   *streams = (int)(s * per_block);
   const size_t off = align_up((size_t)rows * (size_t)(*streams) * (*C) * sizeof(u64), 256);
   *off_counts = off;
-  *total = align_up(off + (size_t)rows * (size_t)(*streams) * sizeof(int), 256);
+  // counts, then one u32 per query: the best stream threshold (row-level bound for finalize's prefilter)
+  *total = align_up(align_up(off + (size_t)rows * (size_t)(*streams) * sizeof(int), 256) + (size_t)rows * sizeof(u32), 256);
 }
 
 int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
@@ -741,14 +742,18 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
   if (!workspace || workspace_bytes < tot) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, tot);
   unsigned char* ws = (unsigned char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  // per query: max over its streams of the stream's k-th best score (every stream that pruned holds >= k
+  // docs at or above its threshold, so the row's k-th best is at least the largest of them)
+  u32* row_tau = (u32*)(ws + align_up(oc + (size_t)Bq * ns * sizeof(int), 256));
+  if (cudaMemsetAsync(row_tau, 0, (size_t)Bq * sizeof(u32), st) != cudaSuccess) return fail(CCR_ECUDA, "memset bm25 bounds");
   int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
-                                        q_terms, Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st)
+                                        q_terms, Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), row_tau, nullptr, 0, st)
                 : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
                                    Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
   if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   FinalizeParams fp = {};
   fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = ns; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
-  fp.g_tau = nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
+  fp.g_tau = warp ? row_tau : nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
   fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
   if (lr) return fail(CCR_ECUDA, "finalize launch failed: %s", cudaGetErrorString((cudaError_t)lr));
@@ -767,7 +772,7 @@ int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, co
   int S, C, ns; size_t oc, tot;
   bm25_plan(Bq, n_docs, 1, warp, &S, &C, &ns, &oc, &tot);
   int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
-                                        q_terms, Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
+                                        q_terms, Bq, n_docs, 1, C, S, nullptr, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
                 : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
                                    Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "bm25 scores launch failed: %s", cudaGetErrorString((cudaError_t)lr));

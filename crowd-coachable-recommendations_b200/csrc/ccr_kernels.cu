@@ -993,7 +993,7 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
 __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_warp_kernel(
     const long long* __restrict__ post_indptr, const int* __restrict__ post_docs, const double* __restrict__ post_val,
     const long long* __restrict__ q_indptr, const int* __restrict__ q_terms, long long N, int k, int C, int S,
-    u64* cand, int* counts, double* dense_out, long long ld_out) {
+    u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out) {
   __shared__ double s_acc[kBmwWarps][kBmwMini];
   __shared__ long long s_cur[kBmwWarps][kBmwMaxTerms];
   __shared__ long long s_end[kBmwWarps][kBmwMaxTerms];
@@ -1113,16 +1113,20 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
     }
     __syncwarp();
   }
-  if (counts && lane == 0) counts[(long long)row * n_streams + stream] = cnt;
+  if (counts && lane == 0) {
+    counts[(long long)row * n_streams + stream] = cnt;
+    // this stream holds >= k docs scoring >= tau_f once it has pruned: a lower bound of the row's k-th best
+    if (row_tau && tau_key != 0ull) atomicMax(row_tau + row, ord32(tau_f));
+  }
 }
 
 int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
                           const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
-                          u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st) {
+                          u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out, cudaStream_t st) {
   if (Bq <= 0 || N <= 0) return 0;
   dim3 grid((unsigned)S, (unsigned)Bq);
   bm25_topk_warp_kernel<<<grid, kBmwWarps * 32, 0, st>>>(post_indptr, post_docs, post_val, q_indptr, q_terms, N, k, C, S,
-                                                        cand, counts, dense_out, ld_out);
+                                                        cand, counts, row_tau, dense_out, ld_out);
   return (int)cudaGetLastError();
 }
 

@@ -164,7 +164,7 @@ constexpr int kBmwDepth = 4;         // batches of 32 postings in flight per war
 constexpr int kBmwBlocksPerSm = 5;   // 42.5 KB of static shared memory per block
 int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
                           const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
-                          u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st);
+                          u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out, cudaStream_t st);
 int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,
                         const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
                         cudaStream_t st);
