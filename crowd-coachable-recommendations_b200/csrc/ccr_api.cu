@@ -238,19 +238,22 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
 
 // Bounded-drift lead (item tiles) of the units that stream one item split.  The tiles between the
 // slowest and the fastest unit of every split in flight must stay L2-resident or the followers re-read
-// them from HBM.  Measured on B200 (profiles/r02_lead_sweep.md, 8.84M x 768): a lead of 16 tiles is the
-// best or within noise everywhere except where many splits are in flight with several units each --
-// B=1024: 18 splits x 16 tiles x 393 KB = 113 MB of window against a 126 MB L2, 24.6 GB of DRAM reads for
-// a 13.6 GB table (ncu, profiles/r02_batch_counters.csv) -- there a lead of 8 is 7 % faster.  Leads of
-// 2-4 tiles stall the producers on the polling itself (every tile) and lose 10-30 %.
+// them from HBM: (splits in flight) x lead x tile bytes is held to a budget well inside the 126 MB L2.
+// ncu before this policy (lead 16 everywhere, profiles/r02_batch_counters.csv, r02_select_tc_b512_ncu_raw.csv):
+// B=512 37 splits in flight 18.9 GB of DRAM reads for a 13.6 GB table, B=1024 21-25 GB, B=2048 21.4 GB,
+// B=4096 (4.6 splits in flight) 16.4-17.0 GB.  The poller warp makes tile-granular throttling free for
+// the producer, so small leads no longer cost issue time.
 int default_lead_tiles(const Plan& pl, int D, int sms) {
   const int workers = pl.two_cta ? sms / 2 : sms;
   long long conc = (workers + pl.n_q_tiles - 1) / pl.n_q_tiles;
   if (conc > pl.S) conc = pl.S;
   if (conc < 1) conc = 1;
   const long long tile_bytes = (long long)kITile * D * 2;
-  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 96;
-  return (pl.n_q_tiles >= 4 && conc * 16 * tile_bytes > ((long long)mb << 20)) ? 8 : 16;
+  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 48;
+  long long lead = ((long long)mb << 20) / (conc * tile_bytes);
+  if (lead > 16) lead = 16;
+  if (lead < 3) lead = 3;
+  return (int)lead;
 }
 
 int check_shape(long long B, long long n_items, int D, int k, int flags) {
@@ -381,8 +384,6 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   if (kn.throttle >= 0) use_throttle = kn.throttle != 0;
   sp.lead_tiles = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl, D, device_sm_count()) : 16;
   if (kn.lead >= 1 && kn.lead <= 4096) sp.lead_tiles = kn.lead;
-  sp.lead_every = 1;
-  while (sp.lead_every * 4 <= sp.lead_tiles && sp.lead_every < 8) sp.lead_every *= 2;  // 16 -> 8 (4 -> 2, 2 -> 1)
   if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) sp.progress = (int*)(ws + pl.off_progress);
   if (pl.share_j > 0 || pl.seed_m > 0) {
     sp.g_tau = (u32*)(ws + pl.off_gtau);
@@ -539,7 +540,7 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
     sp.S = splits_tc(sp.n_q_tiles, (n_items + kITile - 1) / kITile, device_sm_count());
     sp.status = (DeviceStatus*)g_status_record;
     sp.dense_out = out; sp.ld_out = ld_out; sp.store_max8 = 0;
-    sp.lead_tiles = 16; sp.lead_every = 8;
+    sp.lead_tiles = 16;
     int lr = launch_select_tc(sp, (cudaStream_t)stream, device_sm_count());
     if (lr) return fail(CCR_ECUDA, "dense tile launch failed (%d)", lr);
     return CCR_OK;

@@ -39,7 +39,7 @@ constexpr int kTcThreads = 384;                 // 3 warpgroups: warps 0..7 sele
                                                 // warps 10..11 idle (whole warpgroups so that setmaxnreg can
                                                 // move registers from the feeders to the selection warps)
 constexpr int kSelRegs = 216, kFeedRegs = 56;
-constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kPollWarp = kEpiWarps + 2;
 constexpr unsigned long long kThrottleGiveUpNs = 2ull * 1000ull * 1000ull;  // 2 ms
 constexpr int kStageKeys = 384;                 // candidate buffers up to this size are pruned in smem
 constexpr int kTmemCols = 512;
@@ -51,7 +51,8 @@ struct __align__(8) TcShared {
   u64 tmem_full[2];
   u64 tmem_empty[2];
   u32 tmem_base;
-  u32 pad;
+  int thr_unit;      // throttle: unit the producer is streaming (-1 none yet, -2 all done); written by the producer
+  u64 thr_pack;      // throttle: (unit << 32) | tiles the producer may have issued; written by the poller warp
   u32 hist[kEpiWarps][256];
   u64 stage[kEpiWarps][kStageKeys];
 };
@@ -445,6 +446,8 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
   const int cid = (int)blockIdx.x / kCta, n_cl = (int)gridDim.x / kCta;  // persistent workers = clusters
 
   if (threadIdx.x == 0) {
+    sh->thr_unit = -1;
+    sh->thr_pack = ~0ull;  // unit tag that matches no unit
     for (int s = 0; s < kStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full[s], 1); mbar_init(&sh->tmem_empty[s], kEpiWarps * kCta); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -489,26 +492,29 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // together.  A leader that is not slowed down by its own L2 misses (the 6-stage pair
         // pipeline hides them) runs away and every follower then misses too: DRAM reads of 7x the
         // table were measured for CTA pairs at B=4096.  So a producer never leads the slowest peer by
-        // more than lead_tiles (progress is published and checked every lead_every tiles).  The lead is
-        // chosen by the host so that (splits in flight) x (lead) item tiles stay well inside L2.  Peers
+        // more than lead_tiles.  The lead is chosen by the host so that (splits in flight) x (lead) item
+        // tiles stay well inside L2; the peers' counters are watched by the poller warp below.  Peers
         // run concurrently because the grid has at most one CTA per SM;
         // should one not be running (shared GPU), the wait gives up after 2 ms and throttling is
         // dropped for the rest of the unit.
         bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
+        if (p.progress != nullptr) {  // tell the poller warp which unit is being streamed
+          asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&sh->thr_unit)), "r"(throttle ? unit : -1) : "memory");
+        }
         for (long long t = t0; t < t1; ++t) {
-          if (throttle && ((t - t0) & (long long)(p.lead_every - 1)) == 0) {
+          if (throttle) {
+            // publish my position (fire and forget), then make sure I am not more than lead_tiles ahead
+            // of the slowest peer: the poller warp keeps (unit, slowest + lead) in shared memory, so this
+            // thread never waits for a global load
             const int mine = (int)(t - t0);
             asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(mine) : "memory");
             unsigned long long w0 = 0;
             for (;;) {
-              int mn = 0x7fffffff;
-              for (int v = peer_lo; v < peer_hi; ++v) {
-                int pv;
-                asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(p.progress + v) : "memory");
-                mn = pv < mn ? pv : mn;
-              }
-              if (mine - mn <= p.lead_tiles) break;
-              __nanosleep(500);
+              u64 a;
+              asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(a) : "r"(smem_u32(&sh->thr_pack)) : "memory");
+              const int allowed = ((int)(a >> 32) == unit) ? (int)(u32)a : p.lead_tiles;  // no report yet: head start
+              if (mine <= allowed) break;
+              __nanosleep(100);
               unsigned long long now;
               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
               if (w0 == 0) w0 = now;
@@ -532,8 +538,44 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
         }
-        if (throttle)  // finished: never hold a peer back
+        if (p.progress != nullptr && (peer_hi - peer_lo) > 1)  // finished: never hold a peer back
           asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(0x3fffffff) : "memory");
+      }
+      if (p.progress != nullptr)
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&sh->thr_unit)), "r"(-2) : "memory");
+    }
+  } else if (warp == kPollWarp) {
+    // ================= throttle poller =================
+    // Units that stream the same item split only share its tiles through L2 while they stay close.  This
+    // warp watches the progress counters of the producer's peers (one lane per peer, in parallel) and
+    // keeps "slowest peer + lead" in shared memory for the producer, which therefore throttles at tile
+    // granularity without ever waiting for a global load itself.
+    if (p.progress != nullptr) {
+      for (;;) {
+        int unit;
+        asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(unit) : "r"(smem_u32(&sh->thr_unit)) : "memory");
+        if (unit == -2) break;
+        if (unit >= 0) {
+          const int u = unit / p.n_q_tiles;
+          int peer_lo = u * p.n_q_tiles, peer_hi = peer_lo + p.n_q_tiles;
+          const int it_lo = (unit / n_cl) * n_cl, it_hi = it_lo + n_cl;
+          peer_lo = peer_lo > it_lo ? peer_lo : it_lo;
+          peer_hi = peer_hi < it_hi ? peer_hi : it_hi;
+          int mn = 0x7fffffff;
+          for (int v = peer_lo + lane; v < peer_hi; v += 32) {
+            int pv;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(p.progress + v) : "memory");
+            mn = pv < mn ? pv : mn;
+          }
+#pragma unroll
+          for (int off = 16; off; off >>= 1) { const int o = __shfl_xor_sync(0xffffffffu, mn, off); mn = o < mn ? o : mn; }
+          if (lane == 0) {
+            const long long allowed = (long long)mn + p.lead_tiles;
+            const u64 pack = ((u64)(u32)unit << 32) | (u64)(u32)(allowed > 0x3fffffff ? 0x3fffffff : (int)allowed);
+            asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"(smem_u32(&sh->thr_pack)), "l"(pack) : "memory");
+          }
+        }
+        __nanosleep(400);
       }
     }
   } else if (warp == kMmaWarp) {
