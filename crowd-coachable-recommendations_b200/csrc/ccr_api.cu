@@ -22,8 +22,8 @@ namespace {
 struct Knobs {
   int mask_exclude = 0, two_cta = -1, split_mult = 0, cap_mult = 0, no_share = 0, no_seed = 0, no_hist = 0;
   long long seed_m = 0;
-  int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0, l2_budget_mb = 0;
-  int bm25_blockwide = 0;
+  int debug = 0, debug_grid = 0, keep_tau = 0, throttle = -1, lead = 0, no_qpad = 0;
+  int bm25_blockwide = 0, thr_mode = -1;
   float debug_tau = 0.f;
 };
 Knobs g_knobs;
@@ -46,8 +46,8 @@ void load_knobs() {
   k.throttle = env_int("CCR_THROTTLE", -1);
   k.lead = env_int("CCR_LEAD", 0);
   k.no_qpad = getenv("CCR_NO_QPAD") != nullptr;
-  k.l2_budget_mb = env_int("CCR_L2_BUDGET_MB", 0);
   k.bm25_blockwide = getenv("CCR_BM25_BLOCKWIDE") != nullptr;
+  k.thr_mode = env_int("CCR_THR_MODE", -1);
   { const char* v = getenv("CCR_DEBUG_TAU"); k.debug_tau = v ? (float)atof(v) : 0.f; }
   g_knobs = k;
 }
@@ -236,25 +236,19 @@ bool make_plan(long long B, long long n_items, int D, int k, long long nnz, long
   return true;
 }
 
-// Bounded-drift lead (item tiles) of the units that stream one item split.  The tiles between the
-// slowest and the fastest unit of every split in flight must stay L2-resident or the followers re-read
-// them from HBM: (splits in flight) x lead x tile bytes is held to a budget well inside the 126 MB L2.
-// ncu before this policy (lead 16 everywhere, profiles/r02_batch_counters.csv, r02_select_tc_b512_ncu_raw.csv):
-// B=512 37 splits in flight 18.9 GB of DRAM reads for a 13.6 GB table, B=1024 21-25 GB, B=2048 21.4 GB,
-// B=4096 (4.6 splits in flight) 16.4-17.0 GB.  The poller warp makes tile-granular throttling free for
-// the producer, so small leads no longer cost issue time.
-int default_lead_tiles(const Plan& pl, int D, int sms) {
-  const int workers = pl.two_cta ? sms / 2 : sms;
-  long long conc = (workers + pl.n_q_tiles - 1) / pl.n_q_tiles;
-  if (conc > pl.S) conc = pl.S;
-  if (conc < 1) conc = 1;
-  const long long tile_bytes = (long long)kITile * D * 2;
-  const int mb = knobs().l2_budget_mb > 0 ? knobs().l2_budget_mb : 48;
-  long long lead = ((long long)mb << 20) / (conc * tile_bytes);
-  if (lead > 16) lead = 16;
-  if (lead < 3) lead = 3;
-  return (int)lead;
-}
+// Bounded-drift throttle of the units that stream one item split (they only share its tiles through L2
+// while they stay close).  Same-box A/B on B200, 8.84M x 768 (profiles/r02_throttle_ab.md):
+//  * who polls: the producer itself every lead/2 tiles ("inline") is fastest up to 16 units per split
+//    (B <= 4096: 42.6 vs 46.0 ms at B=4096, 21.6 vs 28.0 at 2048); from 32 units per split on, reading
+//    32 counters serially stalls the producer and a dedicated poller warp that keeps
+//    "slowest + lead" in shared memory wins (B=8192: 84.9 vs 89.2 ms).
+//  * lead: 16 tiles below 4 units per split (no throttle needed at 2: 6.27 vs 6.30 ms), 8 tiles from
+//    4 units per split on (B=1024 11.71 vs 11.75, 2048 21.6 vs 22.0, 4096 42.6 vs 42.9 ms); leads of 2-4
+//    tiles stall the producers on the polling itself and lose 10-30 %.
+int default_lead_tiles(const Plan& pl) { return pl.n_q_tiles >= 4 ? 8 : 16; }
+//  * single CTAs (odd tile counts, B > 8192) gain from the same throttle: B=640 8.63 vs 9.16 ms, 1152 13.8
+//    vs 14.9, 16384 (poller) 183.1 vs 186.8.
+int default_throttle_poller(const Plan& pl) { return pl.n_q_tiles >= 32 ? 1 : 0; }
 
 int check_shape(long long B, long long n_items, int D, int k, int flags) {
   if (B < 0 || n_items < 0) return fail(CCR_EINVAL, "negative size B=%lld n_items=%lld", B, n_items);
@@ -310,7 +304,7 @@ int ccr_plan_info(int64_t B, int64_t n_items, int D, int k, int64_t mask_nnz, in
   Plan pl;
   make_plan(B, n_items, D, k, mask_nnz, mask_nnz > 0 ? mask_max_row_nnz : -1, flags, &pl);
   const bool seeded = pl.seed_m > 0 && n_items > 0 && !knobs().keep_tau;
-  int lead = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl, D, device_sm_count()) : 0;
+  int lead = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl) : 0;
   if (knobs().lead >= 1 && knobs().lead <= 4096) lead = knobs().lead;
   info8[0] = pl.n_q_tiles;
   info8[1] = pl.S;
@@ -377,13 +371,16 @@ int ccr_score_topk_bf16(const void* q, int64_t B, int64_t ldq, const void* items
   sp.dense_out = nullptr; sp.ld_out = 0; sp.store_max8 = 0;
   sp.progress = nullptr;
   sp.g_hist = nullptr; sp.g_hpar = nullptr;
-  // bounded drift between the units that stream the same item split: default for CTA pairs (their
-  // deeper pipeline lets a leader run away from its followers: 99 GB instead of 15 GB of DRAM reads
-  // at B=4096), opt-in for single CTAs where it was measured to cost more than it saves
-  bool use_throttle = pl.two_cta && pl.n_q_tiles > 1;
+  // bounded drift between the units that stream the same item split (see default_lead_tiles): without
+  // it a leader runs away from its followers and every follower misses L2 too (99 GB instead of 15 GB
+  // of DRAM reads were measured for CTA pairs at B=4096)
+  bool use_throttle = pl.n_q_tiles > 1;
   if (kn.throttle >= 0) use_throttle = kn.throttle != 0;
-  sp.lead_tiles = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl, D, device_sm_count()) : 16;
+  sp.lead_tiles = pl.algo == CCR_ALGO_TCGEN05 ? default_lead_tiles(pl) : 16;
   if (kn.lead >= 1 && kn.lead <= 4096) sp.lead_tiles = kn.lead;
+  sp.lead_every = 1;
+  while (sp.lead_every * 2 <= sp.lead_tiles && sp.lead_every < 8) sp.lead_every *= 2;  // 16 -> 8, 8 -> 8, 4 -> 4
+  sp.throttle_poller = kn.thr_mode >= 0 ? kn.thr_mode : default_throttle_poller(pl);
   if (pl.algo == CCR_ALGO_TCGEN05 && use_throttle) sp.progress = (int*)(ws + pl.off_progress);
   if (pl.share_j > 0 || pl.seed_m > 0) {
     sp.g_tau = (u32*)(ws + pl.off_gtau);
@@ -540,7 +537,7 @@ int ccr_score_dense_f32(const void* q, int64_t B, int64_t ldq, const void* items
     sp.S = splits_tc(sp.n_q_tiles, (n_items + kITile - 1) / kITile, device_sm_count());
     sp.status = (DeviceStatus*)g_status_record;
     sp.dense_out = out; sp.ld_out = ld_out; sp.store_max8 = 0;
-    sp.lead_tiles = 16;
+    sp.lead_tiles = 16; sp.lead_every = 8;
     int lr = launch_select_tc(sp, (cudaStream_t)stream, device_sm_count());
     if (lr) return fail(CCR_ECUDA, "dense tile launch failed (%d)", lr);
     return CCR_OK;

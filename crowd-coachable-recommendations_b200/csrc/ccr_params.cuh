@@ -54,6 +54,8 @@ struct SelectParams {
   // tiles L2-resident so the table is read from HBM once): tiles issued so far, per unit
   int* progress;  // [n_units], zeroed per call; null = off
   int lead_tiles; // max lead (item tiles) of a producer over the slowest unit on the same split
+  int lead_every; // inline throttle: progress is published / checked every lead_every tiles (power of two)
+  int throttle_poller;  // 1: a dedicated warp watches the peers (tile-granular), 0: the producer polls inline
   // store mode: write fp32 scores instead of selecting (dense score tiles for as_tensor / _argsort).
   // With store_max8 (threshold seeding pre-pass) only the best score of every 8 consecutive items is
   // written: the k-th largest of those group maxima is a lower bound of the k-th largest item score,

@@ -499,10 +499,33 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         // dropped for the rest of the unit.
         bool throttle = p.progress != nullptr && (peer_hi - peer_lo) > 1;
         if (p.progress != nullptr) {  // tell the poller warp which unit is being streamed
-          asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&sh->thr_unit)), "r"(throttle ? unit : -1) : "memory");
+          asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(&sh->thr_unit)),
+                       "r"((throttle && p.throttle_poller) ? unit : -1) : "memory");
         }
+        const int n_peers_inline = peer_hi - peer_lo;
         for (long long t = t0; t < t1; ++t) {
-          if (throttle) {
+          if (throttle && !p.throttle_poller) {
+            // inline variant: every lead_every tiles publish my position and read the peers' myself
+            if (((t - t0) & (long long)(p.lead_every - 1)) == 0) {
+              const int mine = (int)(t - t0);
+              asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p.progress + unit), "r"(mine) : "memory");
+              unsigned long long w0 = 0;
+              for (;;) {
+                int mn = 0x7fffffff;
+                for (int v = 0; v < n_peers_inline; ++v) {
+                  int pv;
+                  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(pv) : "l"(p.progress + peer_lo + v) : "memory");
+                  mn = pv < mn ? pv : mn;
+                }
+                if (mine - mn <= p.lead_tiles) break;
+                __nanosleep(500);
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (w0 == 0) w0 = now;
+                else if (now - w0 > kThrottleGiveUpNs) { throttle = false; break; }  // never depend on a peer
+              }
+            }
+          } else if (throttle) {
             // publish my position (fire and forget), then make sure I am not more than lead_tiles ahead
             // of the slowest peer: the poller warp keeps (unit, slowest + lead) in shared memory, so this
             // thread never waits for a global load
