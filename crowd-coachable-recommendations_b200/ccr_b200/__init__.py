@@ -9,11 +9,12 @@ Public surface (mirrors the reference's call sites for this path):
 * ``al_rank.rank_step`` / ``build_requests`` ...           <- scripts/al_0_rank.py:107-218
 * ``BM25`` / ``ranking_bm25``                             <- scripts/bm_25.py, scripts/ms_marco_eval.py:165-186
 * ``EmbeddingTable`` / ``ShardedIndex``                    (residency + row-sharding layer)
-* ``score_topk`` / ``merge_topk``                          (thin wrappers of the C ABI)
+* ``score_topk`` / ``merge_topk`` / ``merge_topk_keys`` / ``argsort_scores`` / ``first_hit_rank``
+                                                           (thin wrappers of the C ABI)
 """
 from ._lib import ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05, MASK_ADD, MASK_NONE, MASK_SET, LIB_PATH  # noqa: F401
-from .engine import (SparseMask, device_status, ingest_rows, merge_topk, merge_topk_keys, score_dense,  # noqa: F401
-                     score_topk, synchronize, topk_dense)
+from .engine import (SparseMask, argsort_scores, device_status, first_hit_rank, ingest_rows, merge_topk,  # noqa: F401
+                     merge_topk_keys, score_dense, score_topk, synchronize, topk_dense, unpack_topk_keys)
 from .table import EmbeddingTable  # noqa: F401
 from .score_array import (  # noqa: F401
     ElementWiseExpression,
@@ -34,7 +35,9 @@ from .ranking import (  # noqa: F401
     cos_sim,
     generate_embeddings,
     generate_embeddings_device,
+    RankingProfile,
     mrr_at_k,
+    qrels_csr,
     ranking,
     ranking_sharded,
     ranking_tensors,
