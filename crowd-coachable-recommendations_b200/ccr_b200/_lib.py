@@ -14,7 +14,7 @@ ALGO_AUTO, ALGO_SIMT, ALGO_TCGEN05 = 0, 1, 2
 FLAG_ALLOW_SHORT = 0x10
 FLAG_PACKED_KEYS = 0x20
 MAX_K = 2048
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 OK, EINVAL, EUNSUPPORTED, EWORKSPACE, ECUDA, EK_RANGE = 0, -1, -2, -3, -4, -5
 
@@ -42,6 +42,8 @@ EXPORTS = [
     "ccr_topk_dense_workspace_bytes",
     "ccr_topk_dense_f32",
     "ccr_bm25_build_impacts",
+    "ccr_bm25_head_row_pitch",
+    "ccr_bm25_build_head_rows",
     "ccr_bm25_topk_workspace_bytes",
     "ccr_bm25_topk",
     "ccr_bm25_scores_f64",
@@ -117,9 +119,13 @@ def lib():
     L.ccr_bm25_topk_workspace_bytes.restype = sz
     L.ccr_bm25_topk_workspace_bytes.argtypes = [i64, i64, i32]
     L.ccr_bm25_topk.restype = i32
-    L.ccr_bm25_topk.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]
+    L.ccr_bm25_topk.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i32, vp, vp, vp, sz, vp]
     L.ccr_bm25_scores_f64.restype = i32
-    L.ccr_bm25_scores_f64.argtypes = [vp, vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]
+    L.ccr_bm25_scores_f64.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, i64, vp]
+    L.ccr_bm25_head_row_pitch.restype = i64
+    L.ccr_bm25_head_row_pitch.argtypes = [i64]
+    L.ccr_bm25_build_head_rows.restype = i32
+    L.ccr_bm25_build_head_rows.argtypes = [vp, vp, vp, vp, i32, i64, i64, vp, vp, vp]
     if L.ccr_abi_version() != ABI_VERSION:
         raise RuntimeError("libccr_b200 ABI version mismatch")
     _lib = L

@@ -22,19 +22,28 @@ RANKING_TOPN = 1001  # scripts/ms_marco_eval.py:182
 QUERY_CHUNK = 4096   # queries per fused call
 WARP_KERNEL_MAX_TERMS = 16  # libccr_b200: kBmwMaxTerms
 MAX_QUERY_TERMS = 512
+HEAD_DF_FRACTION = 0.25     # terms present in at least this share of the docs also get a dense float64 row
+HEAD_MAX_TERMS = 64
+HEAD_MAX_BYTES = 4 << 30
 
 
 class BM25(object):
     """Same constructor, ``fit``, ``cache`` and ``transform`` as scripts/bm_25.py:9-45."""
 
-    def __init__(self, b=0.75, k1=1.6, device="cuda"):
+    def __init__(self, b=0.75, k1=1.6, device="cuda", head_df_fraction=HEAD_DF_FRACTION):
+        """``head_df_fraction``: vocabulary terms that occur in at least this share of the cached
+        documents (stop words) additionally get a dense float64 row on the device, which the kernels
+        add with coalesced loads instead of walking the posting list (``None`` / 0: postings only).
+        The scores are bit-identical either way."""
         from sklearn.feature_extraction.text import TfidfVectorizer
 
         self.vectorizer = TfidfVectorizer(norm=None, smooth_idf=False)
         self.b = b
         self.k1 = k1
         self.device = torch.device(device)
+        self.head_df_fraction = head_df_fraction
         self._impacts_stale = True
+        self._head_slot = self._head_rows = None
 
     # ---- reference API -------------------------------------------------------------------
     def fit(self, X):
@@ -96,8 +105,46 @@ class BM25(object):
                                                    d_idf.data_ptr(), d_norm.data_ptr(), float(k1), n_terms, nnz,
                                                    self._val.data_ptr(), _stream_ptr(dev))
         _lib.check(rc)
+        self._build_head_rows()
         torch.cuda.current_stream(dev).synchronize()  # d_norm / d_idf are released on return
         self._impacts_stale = False
+
+    def head_terms(self):
+        """Vocabulary ids of the terms that get a dense row: df >= head_df_fraction * N, the most frequent
+        first, at most HEAD_MAX_TERMS of them and HEAD_MAX_BYTES of rows."""
+        N = self.n_docs
+        if not self.head_df_fraction or N == 0:
+            return np.zeros(0, np.int32)
+        df = np.diff(self.last_csc_X.indptr)
+        cand = np.nonzero(df >= max(1.0, self.head_df_fraction * N))[0]
+        cand = cand[np.argsort(-df[cand], kind="stable")]
+        pitch = int(_lib.lib().ccr_bm25_head_row_pitch(N))
+        limit = min(HEAD_MAX_TERMS, HEAD_MAX_BYTES // max(1, pitch * 8))
+        return np.ascontiguousarray(cand[:limit], dtype=np.int32)
+
+    def _build_head_rows(self):
+        self._head_slot = self._head_rows = None
+        terms = self.head_terms()
+        if terms.size == 0:
+            return
+        dev, N = self.device, self.n_docs
+        L = _lib.lib()
+        n_terms = self._indptr.numel() - 1
+        d_terms = torch.as_tensor(terms).to(dev)
+        slot = torch.empty(n_terms, dtype=torch.int32, device=dev)
+        rows = torch.empty((terms.size, int(L.ccr_bm25_head_row_pitch(N))), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.ccr_bm25_build_head_rows(self._indptr.data_ptr(), self._docs.data_ptr(), self._val.data_ptr(),
+                                            d_terms.data_ptr(), int(terms.size), n_terms, N, slot.data_ptr(),
+                                            rows.data_ptr(), _stream_ptr(dev))
+        _lib.check(rc)
+        torch.cuda.current_stream(dev).synchronize()  # d_terms is released on return
+        self._head_slot, self._head_rows = slot, rows
+
+    def _head_ptrs(self):
+        if self._head_rows is None:
+            return None, None
+        return self._head_slot.data_ptr(), self._head_rows.data_ptr()
 
     def encode_queries(self, texts):
         """texts -> (q_indptr int64 [B+1], q_terms int32, longest row): the DISTINCT vocabulary terms
@@ -126,7 +173,7 @@ class BM25(object):
         d_indptr, d_terms, longest = self._device_queries(texts)
         with torch.cuda.device(dev):
             rc = _lib.lib().ccr_bm25_scores_f64(self._indptr.data_ptr(), self._docs.data_ptr(), self._val.data_ptr(),
-                                                d_indptr.data_ptr(), d_terms.data_ptr(), longest, B, N,
+                                                *self._head_ptrs(), d_indptr.data_ptr(), d_terms.data_ptr(), longest, B, N,
                                                 out.data_ptr(), N, _stream_ptr(dev))
         _lib.check(rc)
         return out
@@ -168,7 +215,8 @@ class BM25(object):
                     need = L.ccr_bm25_topk_workspace_bytes(n_q, N, k)
                     ws = workspace.get(dev, max(need, 256))
                     rc = L.ccr_bm25_topk(self._indptr.data_ptr(), self._docs.data_ptr(), self._val.data_ptr(),
-                                         d_indptr.data_ptr(), d_terms.data_ptr(), int(lengths[rows].max()), n_q, N, k,
+                                         *self._head_ptrs(), d_indptr.data_ptr(), d_terms.data_ptr(),
+                                         int(lengths[rows].max()), n_q, N, k,
                                          res_s.data_ptr(), res_i.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
                 _lib.check(rc)
                 if not whole:

@@ -658,13 +658,18 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
 
 // ---- BM25 (lexical sibling of the dense path) ----
 // warp = true: the warp-private kernel (S doc splits per query x kBmwWarps independent streams each);
-// false: the block-wide kernel (queries with more than kBmwMaxTerms distinct terms).  *streams = candidate
+// false: the block-wide kernel (queries with more than kBmwMaxTerms distinct terms).  streams = candidate
 // lists per query handed to finalize.
-static void bm25_plan(long long Bq, long long N, int k, bool warp, int* S, int* C, int* streams, size_t* off_counts,
-                      size_t* total) {
+struct Bm25Plan {
+  int S, C, streams;
+  size_t off_counts, off_tau, total;
+};
+
+static Bm25Plan bm25_plan(long long Bq, long long N, int k, bool warp) {
   const int sms = device_sm_count();
   const long long rows = Bq > 0 ? Bq : 1;
   long long s, per_block = 1;
+  Bm25Plan pl = {};
   if (warp) {
     // one resident set of blocks; finer doc splits were measured slower (more streams for finalize to
     // merge and more cursor searches than the better balance across Zipf queries buys: 42.9 ms at 1x,
@@ -674,21 +679,22 @@ static void bm25_plan(long long Bq, long long N, int k, bool warp, int* S, int* 
     if (s * kBmwWarps > minis) s = (minis + kBmwWarps - 1) / kBmwWarps;
     if (s > 1024 / kBmwWarps) s = 1024 / kBmwWarps;  // finalize: kFinMaxStreams
     per_block = kBmwWarps;
-    *C = cand_capacity(k, kBmwMini);
+    pl.C = cand_capacity(k, kBmwMini);
   } else {
     s = ((long long)kBmBlocksPerSm * sms + rows - 1) / rows;  // blocks resident per SM
     const long long chunks = (N + kBmChunk - 1) / kBmChunk;
     if (s > chunks) s = chunks;
     if (s > 1024) s = 1024;  // finalize: kFinMaxStreams
-    *C = cand_capacity(k, kBmSlack);
+    pl.C = cand_capacity(k, kBmSlack);
   }
   if (s < 1) s = 1;
-  *S = (int)s;
-  *streams = (int)(s * per_block);
-  const size_t off = align_up((size_t)rows * (size_t)(*streams) * (*C) * sizeof(u64), 256);
-  *off_counts = off;
+  pl.S = (int)s;
+  pl.streams = (int)(s * per_block);
+  pl.off_counts = align_up((size_t)rows * (size_t)pl.streams * pl.C * sizeof(u64), 256);
   // counts, then one u32 per query: the best stream threshold (row-level bound for finalize's prefilter)
-  *total = align_up(align_up(off + (size_t)rows * (size_t)(*streams) * sizeof(int), 256) + (size_t)rows * sizeof(u32), 256);
+  pl.off_tau = align_up(pl.off_counts + (size_t)rows * (size_t)pl.streams * sizeof(int), 256);
+  pl.total = align_up(pl.off_tau + (size_t)rows * sizeof(u32), 256);
+  return pl;
 }
 
 int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
@@ -705,10 +711,9 @@ int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs,
 
 size_t ccr_bm25_topk_workspace_bytes(int64_t Bq, int64_t n_docs, int k) {
   if (Bq < 0 || n_docs < 0 || k < 1 || k > CCR_MAX_K) return 0;
-  int S, C, ns; size_t oc, tot_w, tot_b;   // the caller does not say how long the queries are: room for either kernel
-  bm25_plan(Bq, n_docs, k, true, &S, &C, &ns, &oc, &tot_w);
-  bm25_plan(Bq, n_docs, k, false, &S, &C, &ns, &oc, &tot_b);
-  return tot_w > tot_b ? tot_w : tot_b;
+  // the caller does not say how long the queries are: room for either kernel
+  const size_t tw = bm25_plan(Bq, n_docs, k, true).total, tb = bm25_plan(Bq, n_docs, k, false).total;
+  return tw > tb ? tw : tb;
 }
 
 static int bm25_check(const int64_t* post_indptr, const int64_t* q_indptr, const int32_t* q_terms, int64_t Bq,
@@ -724,33 +729,59 @@ static int bm25_check(const int64_t* post_indptr, const int64_t* q_indptr, const
   return CCR_OK;
 }
 
+int64_t ccr_bm25_head_row_pitch(int64_t n_docs) {  // whole mini-chunks of the warp-private kernel
+  return n_docs < 0 ? 0 : (n_docs + kBmwMini - 1) / kBmwMini * kBmwMini;
+}
+
+int ccr_bm25_build_head_rows(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                             const int32_t* head_terms, int n_head, int64_t n_terms, int64_t n_docs,
+                             int32_t* head_slot, double* head_rows, void* stream) {
+  if (n_head < 0 || n_terms < 0 || n_docs < 0) return fail(CCR_EINVAL, "bad bm25 head-row shape");
+  if (n_terms > 0 && !head_slot) return fail(CCR_EINVAL, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_terms > 0 && cudaMemsetAsync(head_slot, 0xFF, (size_t)n_terms * sizeof(int32_t), st) != cudaSuccess)  // all -1
+    return fail(CCR_ECUDA, "memset bm25 head slots");
+  if (n_head == 0) return CCR_OK;
+  if (!post_indptr || !post_docs || !post_val || !head_terms || !head_rows) return fail(CCR_EINVAL, "null pointer");
+  int lr = launch_bm25_head_slots(head_terms, n_head, head_slot, st);
+  if (lr) return fail(CCR_ECUDA, "bm25 head slots launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  lr = launch_bm25_head_rows((const long long*)post_indptr, post_docs, post_val, head_terms, n_head,
+                             ccr_bm25_head_row_pitch(n_docs), head_rows, st);
+  if (lr) return fail(CCR_ECUDA, "bm25 head rows launch failed: %s", cudaGetErrorString((cudaError_t)lr));
+  return CCR_OK;
+}
+
 int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                  const int32_t* head_slot, const double* head_rows,
                   const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
                   int64_t n_docs, int k, float* out_scores, int64_t* out_ids, void* workspace,
                   size_t workspace_bytes, void* stream) {
   int rc = bm25_check(post_indptr, q_indptr, q_terms, Bq, n_docs, max_query_terms);
   if (rc) return rc;
+  if ((head_slot == nullptr) != (head_rows == nullptr)) return fail(CCR_EINVAL, "head_slot and head_rows go together");
   if (k < 1 || k > CCR_MAX_K) return fail(CCR_EUNSUPPORTED, "k=%d outside [1,%d]", k, CCR_MAX_K);
   if (k > n_docs) return fail(CCR_EK_RANGE, "selected index k out of range (k=%d > n=%lld)", k, (long long)n_docs);
   if (Bq == 0) return CCR_OK;
   if (!out_scores || !out_ids) return fail(CCR_EINVAL, "null pointer");
   const bool warp = max_query_terms <= kBmwMaxTerms && !knobs().bm25_blockwide;
-  int S, C, ns; size_t oc, tot;
-  bm25_plan(Bq, n_docs, k, warp, &S, &C, &ns, &oc, &tot);
-  if (!workspace || workspace_bytes < tot) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, tot);
+  const Bm25Plan pl = bm25_plan(Bq, n_docs, k, warp);
+  if (!workspace || workspace_bytes < pl.total) return fail(CCR_EWORKSPACE, "workspace %zu < %zu", workspace_bytes, pl.total);
   unsigned char* ws = (unsigned char*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
+  const long long* pi = (const long long*)post_indptr;
+  const long long* qi = (const long long*)q_indptr;
+  u64* cand = (u64*)ws;
+  int* counts = (int*)(ws + pl.off_counts);
   // per query: max over its streams of the stream's k-th best score (every stream that pruned holds >= k
   // docs at or above its threshold, so the row's k-th best is at least the largest of them)
-  u32* row_tau = (u32*)(ws + align_up(oc + (size_t)Bq * ns * sizeof(int), 256));
+  u32* row_tau = (u32*)(ws + pl.off_tau);
   if (cudaMemsetAsync(row_tau, 0, (size_t)Bq * sizeof(u32), st) != cudaSuccess) return fail(CCR_ECUDA, "memset bm25 bounds");
-  int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
-                                        q_terms, Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), row_tau, nullptr, 0, st)
-                : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
-                                   Bq, n_docs, k, C, S, (u64*)ws, (int*)(ws + oc), nullptr, 0, st);
+  int lr = warp ? launch_bm25_topk_warp(pi, post_docs, post_val, head_slot, head_rows, ccr_bm25_head_row_pitch(n_docs), qi,
+                                        q_terms, Bq, n_docs, k, pl.C, pl.S, cand, counts, row_tau, nullptr, 0, st)
+                : launch_bm25_topk(pi, post_docs, post_val, qi, q_terms, Bq, n_docs, k, pl.C, pl.S, cand, counts, nullptr, 0, st);
   if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   FinalizeParams fp = {};
-  fp.B = (int)Bq; fp.k = k; fp.C = C; fp.S = ns; fp.cand = (u64*)ws; fp.counts = (int*)(ws + oc);
+  fp.B = (int)Bq; fp.k = k; fp.C = pl.C; fp.S = pl.streams; fp.cand = cand; fp.counts = counts;
   fp.g_tau = warp ? row_tau : nullptr; fp.drop_cols = nullptr; fp.mask_indptr = nullptr; fp.ovr_hi = nullptr; fp.ovr_lo = nullptr;
   fp.id_offset = 0; fp.out_keys = nullptr; fp.out_scores = out_scores; fp.out_scores64 = nullptr; fp.out_ids = (long long*)out_ids;
   lr = launch_finalize(fp, st);
@@ -759,20 +790,22 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
 }
 
 int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                        const int32_t* head_slot, const double* head_rows,
                         const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
                         int64_t n_docs, double* scores, int64_t ld, void* stream) {
   int rc = bm25_check(post_indptr, q_indptr, q_terms, Bq, n_docs, max_query_terms);
   if (rc) return rc;
+  if ((head_slot == nullptr) != (head_rows == nullptr)) return fail(CCR_EINVAL, "head_slot and head_rows go together");
   if (ld < n_docs) return fail(CCR_EINVAL, "ld < n_docs");
   if (Bq == 0 || n_docs == 0) return CCR_OK;
   if (!scores) return fail(CCR_EINVAL, "null pointer");
   const bool warp = max_query_terms <= kBmwMaxTerms && !knobs().bm25_blockwide;
-  int S, C, ns; size_t oc, tot;
-  bm25_plan(Bq, n_docs, 1, warp, &S, &C, &ns, &oc, &tot);
-  int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr,
-                                        q_terms, Bq, n_docs, 1, C, S, nullptr, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
+  const Bm25Plan pl = bm25_plan(Bq, n_docs, 1, warp);
+  int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, head_slot, head_rows,
+                                        ccr_bm25_head_row_pitch(n_docs), (const long long*)q_indptr,
+                                        q_terms, Bq, n_docs, 1, pl.C, pl.S, nullptr, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
                 : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
-                                   Bq, n_docs, 1, C, S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
+                                   Bq, n_docs, 1, pl.C, pl.S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "bm25 scores launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;
 }

@@ -992,12 +992,13 @@ int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const d
 // =======================================================================================
 __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_warp_kernel(
     const long long* __restrict__ post_indptr, const int* __restrict__ post_docs, const double* __restrict__ post_val,
+    const int* __restrict__ head_slot, const double* __restrict__ head_rows, long long ld_head,
     const long long* __restrict__ q_indptr, const int* __restrict__ q_terms, long long N, int k, int C, int S,
     u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out) {
-  __shared__ double s_acc[kBmwWarps][kBmwMini];
+  __shared__ __align__(16) double s_acc[kBmwWarps][kBmwMini];
   __shared__ long long s_cur[kBmwWarps][kBmwMaxTerms];
   __shared__ long long s_end[kBmwWarps][kBmwMaxTerms];
-  __shared__ int s_nxt[kBmwWarps][kBmwMaxTerms];
+  __shared__ int s_nxt[kBmwWarps][kBmwMaxTerms];   // head terms: -(slot + 1)
   __shared__ u32 s_hist[kBmwWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = blockIdx.y;
@@ -1014,20 +1015,27 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
   long long* pend = s_end[warp];
   int* nxt = s_nxt[warp];
   u64* buf = cand ? cand + ((long long)row * n_streams + stream) * C : nullptr;
-  if (lane < T && d0 < d1) {  // cursor of term `lane`: first posting with doc >= d0
+  if (lane < T && d0 < d1) {
     const int term = q_terms[tb + lane];
-    long long lo = post_indptr[term];
-    const long long end = post_indptr[term + 1];
-    long long hi = end;
-    while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)post_docs[mid] < d0) lo = mid + 1; else hi = mid; }
-    cur[lane] = lo;
-    pend[lane] = end;
-    nxt[lane] = lo < end ? post_docs[lo] : 0x7fffffff;
+    const int slot = head_slot ? __ldg(head_slot + term) : -1;
+    if (slot >= 0) {
+      // head term: its values are read from a dense row (no cursor, no doc ids)
+      cur[lane] = 0; pend[lane] = 0; nxt[lane] = -(slot + 1);
+    } else {  // cursor of term `lane`: first posting with doc >= d0
+      long long lo = post_indptr[term];
+      const long long end = post_indptr[term + 1];
+      long long hi = end;
+      while (lo < hi) { const long long mid = (lo + hi) >> 1; if ((long long)post_docs[mid] < d0) lo = mid + 1; else hi = mid; }
+      cur[lane] = lo;
+      pend[lane] = end;
+      nxt[lane] = lo < end ? post_docs[lo] : 0x7fffffff;
+    }
   }
   __syncwarp();
   int cnt = 0;             // warp-uniform
   float tau_f = -INFINITY;
   u64 tau_key = 0ull;
+  bool pruned = false;
   for (long long c0 = d0; c0 < d1; c0 += kBmwMini) {
     const long long c1 = c0 + kBmwMini < d1 ? c0 + kBmwMini : d1;
     const int len = (int)(c1 - c0);
@@ -1035,7 +1043,29 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
     for (int j = 0; j < kBmwMini / 32; ++j) acc[j * 32 + lane] = 0.0;
     __syncwarp();
     for (int t = 0; t < T; ++t) {
-      if ((long long)nxt[t] >= c1) continue;  // warp-uniform: shared-memory value
+      const int nx = nxt[t];
+      if ((long long)nx >= c1) continue;  // warp-uniform: shared-memory value
+      if (nx < 0) {
+        // head term: 512 consecutive float64 values of its dense row (zero where the doc lacks the term:
+        // x + 0.0 == x bit for bit, scores being sums of positive values from +0.0) -- independent,
+        // fully coalesced 16-byte loads, nothing to search and nothing to vote on
+        const double2* r = reinterpret_cast<const double2*>(head_rows + (long long)(-nx - 1) * ld_head + c0);
+        double2* a2 = reinterpret_cast<double2*>(acc);
+#pragma unroll
+        for (int h = 0; h < kBmwMini / 256; ++h) {
+          double2 x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = __ldg(r + h * 128 + j * 32 + lane);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            double2 a = a2[h * 128 + j * 32 + lane];
+            a.x += x[j].x; a.y += x[j].y;
+            a2[h * 128 + j * 32 + lane] = a;
+          }
+        }
+        __syncwarp();
+        continue;
+      }
       long long e = cur[t];
       const long long end = pend[t];
       bool more = true;
@@ -1105,10 +1135,23 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
       }
       __syncwarp();
       if (cnt > C - kBmwMini) {  // C >= 2k + kBmwMini: room for the next mini-chunk after a prune
-        const u64 pivot = warp_prune(buf, cnt, k, smem_addr(s_hist[warp]), 0u);
-        cnt = k;
-        tau_key = pivot;
-        tau_f = key_score(pivot);
+        // one histogram pass over the keys (keeps everything at or above the bucket where the count from
+        // the top reaches k: a score threshold with >= k docs at or above it); tie-heavy or crowded
+        // buffers fall back to the exact radix select
+        u32 pivot_ord = 0u, j_ord = 0u;
+        int kept = 0;
+        if (warp_prune_hist<false>(buf, cnt, k, k, (k + C - kBmwMini) / 2, smem_addr(s_hist[warp]), 0u, &pivot_ord, &kept,
+                                   &j_ord)) {
+          cnt = kept;
+          tau_key = 0ull;
+          tau_f = unord32(pivot_ord);
+        } else {
+          const u64 pivot = warp_prune(buf, cnt, k, smem_addr(s_hist[warp]), 0u);
+          cnt = k;
+          tau_key = pivot;
+          tau_f = key_score(pivot);
+        }
+        pruned = true;
       }
     }
     __syncwarp();
@@ -1116,17 +1159,52 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
   if (counts && lane == 0) {
     counts[(long long)row * n_streams + stream] = cnt;
     // this stream holds >= k docs scoring >= tau_f once it has pruned: a lower bound of the row's k-th best
-    if (row_tau && tau_key != 0ull) atomicMax(row_tau + row, ord32(tau_f));
+    if (row_tau && pruned) atomicMax(row_tau + row, ord32(tau_f));
   }
 }
 
 int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
+                          const int* head_slot, const double* head_rows, long long ld_head,
                           const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
                           u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out, cudaStream_t st) {
   if (Bq <= 0 || N <= 0) return 0;
   dim3 grid((unsigned)S, (unsigned)Bq);
-  bm25_topk_warp_kernel<<<grid, kBmwWarps * 32, 0, st>>>(post_indptr, post_docs, post_val, q_indptr, q_terms, N, k, C, S,
-                                                        cand, counts, row_tau, dense_out, ld_out);
+  bm25_topk_warp_kernel<<<grid, kBmwWarps * 32, 0, st>>>(post_indptr, post_docs, post_val, head_slot, head_rows, ld_head,
+                                                        q_indptr, q_terms, N, k, C, S, cand, counts, row_tau, dense_out,
+                                                        ld_out);
+  return (int)cudaGetLastError();
+}
+
+// Dense float64 rows of the head terms (built once per fit / cache): rows[slot, doc] = post_val of
+// (head_terms[slot], doc), 0 elsewhere.  One block per head term.
+__global__ void __launch_bounds__(256) bm25_head_rows_kernel(const long long* __restrict__ post_indptr,
+                                                             const int* __restrict__ post_docs,
+                                                             const double* __restrict__ post_val,
+                                                             const int* __restrict__ head_terms, long long ld_head,
+                                                             double* __restrict__ rows) {
+  const int term = head_terms[blockIdx.x];
+  double* r = rows + (long long)blockIdx.x * ld_head;
+  const long long e0 = post_indptr[term], e1 = post_indptr[term + 1];
+  for (long long e = e0 + threadIdx.x; e < e1; e += 256) r[post_docs[e]] = post_val[e];
+}
+
+__global__ void bm25_head_slots_kernel(const int* __restrict__ head_terms, int n_head, int* __restrict__ head_slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_head) head_slot[head_terms[i]] = i;
+}
+
+int launch_bm25_head_slots(const int* head_terms, int n_head, int* head_slot, cudaStream_t st) {
+  if (n_head <= 0) return 0;
+  bm25_head_slots_kernel<<<(n_head + 127) / 128, 128, 0, st>>>(head_terms, n_head, head_slot);
+  return (int)cudaGetLastError();
+}
+
+int launch_bm25_head_rows(const long long* post_indptr, const int* post_docs, const double* post_val,
+                          const int* head_terms, int n_head, long long ld_head, double* rows, cudaStream_t st) {
+  if (n_head <= 0) return 0;
+  cudaError_t e = cudaMemsetAsync(rows, 0, (size_t)n_head * (size_t)ld_head * sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  bm25_head_rows_kernel<<<(unsigned)n_head, 256, 0, st>>>(post_indptr, post_docs, post_val, head_terms, ld_head, rows);
   return (int)cudaGetLastError();
 }
 

@@ -547,15 +547,18 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
           for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&sh->empty[stage], phase ^ 1u, p.status, 100 + stage);
             unsigned char* sa = smem + (size_t)stage * kStageBytes;
+            // CCR_DEBUG & 1024 (experiment, results invalid): stream the query operand only for the first
+            // tile of a unit -- what the pipeline would cost if the query tile were resident on chip
+            const bool skip_q = (p.debug & 1024) && t > t0;
             if (kCta == 2) {
               // both CTAs' bytes are accounted on the leader's barrier; only the leader arms it
-              if (crank == 0) mbar_expect_tx(&sh->full[stage], 2 * kStageBytes);
+              if (crank == 0) mbar_expect_tx(&sh->full[stage], 2 * (skip_q ? G::kItemBytes : kStageBytes));
               const u32 lbar = mapa_u32(&sh->full[stage], 0);
-              tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar);
+              if (!skip_q) tma_load_2d_2cta(sa, &tmap_q, kb * kKBlock, qt * kQRows + crank * kQTile, lbar);
               tma_load_2d_2cta(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile) + crank * G::kItemRows, lbar);
             } else {
-              mbar_expect_tx(&sh->full[stage], kStageBytes);
-              tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
+              mbar_expect_tx(&sh->full[stage], skip_q ? G::kItemBytes : kStageBytes);
+              if (!skip_q) tma_load_2d(sa, &tmap_q, kb * kKBlock, qt * kQTile, &sh->full[stage]);
               tma_load_2d(sa + kBytesA, &tmap_items, kb * kKBlock, (int)(t * kITile), &sh->full[stage]);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CCR_ABI_VERSION 5
+#define CCR_ABI_VERSION 6
 
 /* error codes */
 #define CCR_OK 0
@@ -236,17 +236,35 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
  * (reference: unspecified); out_scores float32 [Bq,k], out_ids int64 [Bq,k].  The n_docs-long
  * score vector only ever exists chunk-wise in shared memory.  k > n_docs -> CCR_EK_RANGE.
  * ccr_bm25_scores_f64: the dense float64 score rows themselves (BM25.transform drop-in).
+ *
+ * Head terms (optional, hybrid index).  A few vocabulary terms occur in a large share of the documents
+ * (stop words); their posting lists dominate the postings a query batch touches.  For such terms the
+ * caller may additionally keep a DENSE float64 row (post_val at the docs that contain the term, 0
+ * elsewhere; x + 0.0 == x bit for bit, so the sums do not change): the kernels then add the row with
+ * independent coalesced loads instead of walking the list (8 bytes per doc instead of 12 per posting, no
+ * cursor, no searches).  ccr_bm25_build_head_rows fills head_slot int32[n_terms] (slot of a head term,
+ * -1 for every other term) and head_rows float64[n_head, pitch] with pitch = ccr_bm25_head_row_pitch(n_docs)
+ * (n_docs rounded up to the kernel's 512-doc chunk) from the postings of head_terms int32[n_head] (device;
+ * distinct term ids chosen by the caller, e.g. every term with df >= n_docs / 4).  The posting lists stay
+ * complete, so head_slot = head_rows = NULL is always valid (and is what queries of more than 16
+ * distinct terms use).
  */
+int64_t ccr_bm25_head_row_pitch(int64_t n_docs);
+int ccr_bm25_build_head_rows(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
+                             const int32_t* head_terms, int n_head, int64_t n_terms, int64_t n_docs,
+                             int32_t* head_slot, double* head_rows, void* stream);
 int ccr_bm25_build_impacts(const int64_t* post_indptr, const int32_t* post_docs, const float* post_tf,
                            const double* idf, const double* doc_norm, double k1, int64_t n_terms, int64_t nnz,
                            double* post_val, void* stream);
 size_t ccr_bm25_topk_workspace_bytes(int64_t Bq, int64_t n_docs, int k);
 int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
-                  const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                  const int32_t* head_slot, const double* head_rows, const int64_t* q_indptr,
+                  const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
                   int64_t n_docs, int k, float* out_scores, int64_t* out_ids, void* workspace,
                   size_t workspace_bytes, void* stream);
 int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,
-                        const int64_t* q_indptr, const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
+                        const int32_t* head_slot, const double* head_rows, const int64_t* q_indptr,
+                        const int32_t* q_terms, int64_t max_query_terms, int64_t Bq,
                         int64_t n_docs, double* scores, int64_t ld, void* stream);
 
 /* Which kernel ccr_score_topk_bf16 picks under CCR_ALGO_AUTO: CCR_ALGO_SIMT or CCR_ALGO_TCGEN05. */

@@ -75,7 +75,7 @@ def _synthetic(seed, n, q, vocab, doc_len):
 
 @pytest.fixture(params=["auto", "blockwide"])
 def bm25_kernel(request):
-    """auto: queries of <= 32 distinct terms take the warp-private kernel, longer ones the block-wide
+    """auto: queries of <= 16 distinct terms take the warp-private kernel, longer ones the block-wide
     kernel (the batches below hold both kinds); blockwide: everything on the block-wide kernel."""
     from ccr_b200 import _lib
 
@@ -114,6 +114,32 @@ def test_bm25_dense_scores_vs_oracle_many_chunks(ccr):
     dense = model.scores(queries).cpu().numpy()
     for b, text in enumerate(queries):
         np.testing.assert_array_equal(dense[b], ref.transform(text))
+
+
+def test_bm25_head_rows_bit_identical(ccr):
+    """Dense float64 rows for the head terms (hybrid index) change the memory traffic, not a single bit of
+    the scores: postings only == default fraction == nearly every term dense, on the warp-private kernel
+    (short queries) with n_docs not a multiple of the 512-doc chunk."""
+    corpus, queries = _synthetic(17, 33333, 64, vocab=300, doc_len=40)
+    queries = [q for q in queries if len(set(q.split())) <= 16]
+    assert len(queries) >= 20
+    model = ccr.BM25(b=0.75, k1=1.2, head_df_fraction=None).fit(corpus)
+    assert model.head_terms().size == 0
+    want = model.scores(queries).cpu().numpy()
+    ws, wi = model.topk(queries, 1001)
+    ref = O.BM25Ref(b=0.75, k1=1.2).fit(corpus)
+    np.testing.assert_array_equal(want[3], ref.transform(queries[3]))
+    sizes = []
+    for frac in (0.25, 0.05, 1e-4):
+        model.head_df_fraction = frac
+        model._impacts_stale = True
+        got = model.scores(queries).cpu().numpy()
+        sizes.append(model.head_terms().size)
+        assert model._head_rows is not None and model._head_rows.shape[0] == sizes[-1]
+        np.testing.assert_array_equal(got, want)
+        s, i = model.topk(queries, 1001)
+        assert torch.equal(s, ws) and torch.equal(i, wi)
+    assert 0 < sizes[0] <= sizes[1] <= sizes[2] == 64  # capped at HEAD_MAX_TERMS
 
 
 def test_bm25_edge_cases(ccr):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().ccr_abi_version() == _lib.ABI_VERSION == 5
+    assert _lib.lib().ccr_abi_version() == _lib.ABI_VERSION == 6
 
 
 def test_planning_entry_points_work_without_gpu():
