@@ -1000,8 +1000,11 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
   __shared__ long long s_end[kBmwWarps][kBmwMaxTerms];
   __shared__ int s_nxt[kBmwWarps][kBmwMaxTerms];   // head terms: -(slot + 1)
   __shared__ u32 s_hist[kBmwWarps][256];
+  __shared__ u32 s_tau_blk;  // ord32 of the best threshold any of the block's streams has reached (same query)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = blockIdx.y;
+  if (threadIdx.x == 0) s_tau_blk = 0u;
+  __syncthreads();  // the only block barrier: from here on every warp runs on its own
   const int stream = blockIdx.x * kBmwWarps + warp, n_streams = S * kBmwWarps;
   const long long n_mini = (N + kBmwMini - 1) / kBmwMini;
   const long long per = (n_mini + n_streams - 1) / n_streams;
@@ -1121,17 +1124,33 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
       double* o = dense_out + row * ld_out + c0;
       for (int j = lane; j < len; j += 32) o[j] = acc[j];
     } else {
-      for (int base = 0; base < len; base += 32) {
-        const int j = base + lane;
-        bool pass = false;
-        u64 key = 0ull;
-        if (j < len) {
-          const float sc = (float)acc[j];
-          if (sc >= tau_f) { key = make_key(sc, (u32)(c0 + j)); pass = key > tau_key; }
+      // A stream that has pruned holds >= k docs at or above its threshold, so that threshold bounds the
+      // QUERY's k-th best from below: the block's streams share the best one (fewer candidates, fewer
+      // prunes).  Scores equal to a foreign bound are kept (>=); the own exact pivot stays a strict key bound.
+      float tau_eff = tau_f;
+      u64 key_eff = tau_key;
+      {
+        u32 tb;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tb) : "r"(smem_addr(&s_tau_blk)) : "memory");
+        if (tb > ord32(tau_f)) { tau_eff = unord32(tb); key_eff = 0ull; }
+      }
+      // one max over the lane's 16 docs + one vote: does the mini-chunk hold a candidate at all?
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kBmwMini / 32; ++j) mx = fmaxf(mx, (float)acc[j * 32 + lane]);
+      if (__any_sync(0xffffffffu, mx >= tau_eff)) {
+        for (int base = 0; base < len; base += 32) {
+          const int j = base + lane;
+          bool pass = false;
+          u64 key = 0ull;
+          if (j < len) {
+            const float sc = (float)acc[j];
+            if (sc >= tau_eff) { key = make_key(sc, (u32)(c0 + j)); pass = key > key_eff; }
+          }
+          const unsigned m = __ballot_sync(0xffffffffu, pass);
+          if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+          cnt += __popc(m);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, pass);
-        if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
-        cnt += __popc(m);
       }
       __syncwarp();
       if (cnt > C - kBmwMini) {  // C >= 2k + kBmwMini: room for the next mini-chunk after a prune
@@ -1152,6 +1171,7 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
           tau_f = key_score(pivot);
         }
         pruned = true;
+        if (lane == 0) atomicMax(&s_tau_blk, ord32(tau_f));
       }
     }
     __syncwarp();
