@@ -223,3 +223,31 @@ def test_transform_scores_factor_pair_equals_reference_matrix(sim):
     want = O.transform_scores_ref(all_emb, i_to_ptr, j_to_ptr, 16, sim).numpy()
     np.testing.assert_allclose(S.left.c @ S.right.c, want, rtol=1e-5, atol=1e-5)
     assert ccr.fused_plan(S[2:5]).shape == (3, 41)  # row slicing keeps the factor form
+
+
+def test_bench_reference_arm_contract(capsys, monkeypatch):
+    """`bench.py --impl reference`: exactly --warmup + --steps steps of the CPU path, the product arm's
+    `config` dict verbatim, the sample size bounded by a time budget (no GPU involved)."""
+    import argparse
+    import json
+
+    import bench
+
+    assert bench.reference_sample_queries(25, bench.N_ITEMS) == 7      # the driver's 20 + 5 steps
+    assert bench.reference_sample_queries(13, bench.N_ITEMS) == 17     # bench.py's defaults
+    assert bench.reference_sample_queries(2, bench.N_ITEMS) == 32      # capped
+    assert bench.reference_sample_queries(10_000, bench.N_ITEMS) == 1  # never zero
+    calls = []
+    monkeypatch.setattr(bench, "cpu_reference_step", lambda P, n, seed=0: calls.append((n, seed)) or 0.01)
+    monkeypatch.setattr(bench, "host_corpus", lambda n, seed=0: torch.zeros((4, bench.DIM)))
+    monkeypatch.delenv("RANK", raising=False)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    a = argparse.Namespace(gpus=1, steps=4, warmup=2, n_items=50_000, k=100, batch=4096, metric="m", workload="w")
+    bench.run_reference(a)
+    line = json.loads(capsys.readouterr().out)
+    assert (line["impl"], line["steps"], line["warmup"]) == ("reference", 4, 2)
+    assert len(calls) == 6 and len({n for n, _ in calls}) == 1 and calls[0][0] == line["sample_queries_per_step"]
+    assert line["config"] == bench.workload_config(a, 1, 50_000)
+    assert line["config"]["queries_per_step"] == 4096 and "plan" not in line["config"]
+    assert line["e2e"] == {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
