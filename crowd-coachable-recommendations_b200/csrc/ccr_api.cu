@@ -743,9 +743,9 @@ int ccr_bm25_build_head_rows(const int64_t* post_indptr, const int32_t* post_doc
     return fail(CCR_ECUDA, "memset bm25 head slots");
   if (n_head == 0) return CCR_OK;
   if (!post_indptr || !post_docs || !post_val || !head_terms || !head_rows) return fail(CCR_EINVAL, "null pointer");
-  int lr = launch_bm25_head_slots(head_terms, n_head, head_slot, st);
+  int lr = launch_bm25_head_slots(head_terms, n_head, n_terms, head_slot, st);
   if (lr) return fail(CCR_ECUDA, "bm25 head slots launch failed: %s", cudaGetErrorString((cudaError_t)lr));
-  lr = launch_bm25_head_rows((const long long*)post_indptr, post_docs, post_val, head_terms, n_head,
+  lr = launch_bm25_head_rows((const long long*)post_indptr, post_docs, post_val, head_terms, n_head, n_terms,
                              ccr_bm25_head_row_pitch(n_docs), head_rows, st);
   if (lr) return fail(CCR_ECUDA, "bm25 head rows launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;

@@ -1181,6 +1181,32 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
     // this stream holds >= k docs scoring >= tau_f once it has pruned: a lower bound of the row's k-th best
     if (row_tau && pruned) atomicMax(row_tau + row, ord32(tau_f));
   }
+  // A tighter row bound for finalize's prefilter from the block's 8 streams together: every stream
+  // publishes its j-th best score (j = ceil(k / 5)); the 5th largest of those has >= 5 j >= k docs at or
+  // above it.  With it the entries finalize has to look at (~3 k instead of ~8 k for k = 1001) fit its
+  // shared-memory list.
+  if (row_tau) {   // top-k mode (uniform)
+    const int j = (k + kBmwSketchM - 1) / kBmwSketchM;
+    u32 jv = 0u;
+    if (cnt >= j && j >= 1) {
+      __syncwarp();
+      jv = (u32)(warp_select_kth(GlobalKeys{buf}, cnt, j, smem_addr(s_hist[warp])) >> 32);
+    }
+    __shared__ u32 s_jth[kBmwWarps];
+    if (lane == 0) s_jth[warp] = jv;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u32 v[kBmwWarps];
+#pragma unroll
+      for (int i = 0; i < kBmwWarps; ++i) v[i] = s_jth[i];
+#pragma unroll
+      for (int a = 0; a < kBmwSketchM; ++a)      // partial selection sort: v[0..M) = the M largest, descending
+#pragma unroll
+        for (int b = a + 1; b < kBmwWarps; ++b)
+          if (v[b] > v[a]) { const u32 t = v[a]; v[a] = v[b]; v[b] = t; }
+      if (v[kBmwSketchM - 1] != 0u) atomicMax(row_tau + row, v[kBmwSketchM - 1]);
+    }
+  }
 }
 
 int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, const double* post_val,
@@ -1200,31 +1226,37 @@ int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, co
 __global__ void __launch_bounds__(256) bm25_head_rows_kernel(const long long* __restrict__ post_indptr,
                                                              const int* __restrict__ post_docs,
                                                              const double* __restrict__ post_val,
-                                                             const int* __restrict__ head_terms, long long ld_head,
-                                                             double* __restrict__ rows) {
+                                                             const int* __restrict__ head_terms, long long n_terms,
+                                                             long long ld_head, double* __restrict__ rows) {
   const int term = head_terms[blockIdx.x];
+  if (term < 0 || (long long)term >= n_terms) return;  // never trust a caller-supplied id: the row stays zero
   double* r = rows + (long long)blockIdx.x * ld_head;
   const long long e0 = post_indptr[term], e1 = post_indptr[term + 1];
   for (long long e = e0 + threadIdx.x; e < e1; e += 256) r[post_docs[e]] = post_val[e];
 }
 
-__global__ void bm25_head_slots_kernel(const int* __restrict__ head_terms, int n_head, int* __restrict__ head_slot) {
+__global__ void bm25_head_slots_kernel(const int* __restrict__ head_terms, int n_head, long long n_terms,
+                                       int* __restrict__ head_slot) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_head) head_slot[head_terms[i]] = i;
+  if (i >= n_head) return;
+  const int term = head_terms[i];
+  if (term >= 0 && (long long)term < n_terms) head_slot[term] = i;
 }
 
-int launch_bm25_head_slots(const int* head_terms, int n_head, int* head_slot, cudaStream_t st) {
+int launch_bm25_head_slots(const int* head_terms, int n_head, long long n_terms, int* head_slot, cudaStream_t st) {
   if (n_head <= 0) return 0;
-  bm25_head_slots_kernel<<<(n_head + 127) / 128, 128, 0, st>>>(head_terms, n_head, head_slot);
+  bm25_head_slots_kernel<<<(n_head + 127) / 128, 128, 0, st>>>(head_terms, n_head, n_terms, head_slot);
   return (int)cudaGetLastError();
 }
 
 int launch_bm25_head_rows(const long long* post_indptr, const int* post_docs, const double* post_val,
-                          const int* head_terms, int n_head, long long ld_head, double* rows, cudaStream_t st) {
+                          const int* head_terms, int n_head, long long n_terms, long long ld_head, double* rows,
+                          cudaStream_t st) {
   if (n_head <= 0) return 0;
   cudaError_t e = cudaMemsetAsync(rows, 0, (size_t)n_head * (size_t)ld_head * sizeof(double), st);
   if (e != cudaSuccess) return (int)e;
-  bm25_head_rows_kernel<<<(unsigned)n_head, 256, 0, st>>>(post_indptr, post_docs, post_val, head_terms, ld_head, rows);
+  bm25_head_rows_kernel<<<(unsigned)n_head, 256, 0, st>>>(post_indptr, post_docs, post_val, head_terms, n_terms, ld_head,
+                                                          rows);
   return (int)cudaGetLastError();
 }
 

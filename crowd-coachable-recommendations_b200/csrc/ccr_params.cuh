@@ -161,6 +161,7 @@ constexpr int kBmSlack = 1024;     // accumulators ranked between two prune chec
 constexpr int kBmwWarps = 8;
 constexpr int kBmwMini = 512;
 constexpr int kBmwMaxTerms = 16;
+constexpr int kBmwSketchM = 5;       // row bound = the 5th largest of the streams' ceil(k/5)-th best scores
 constexpr int kBmwDepth = 4;         // batches of 32 postings in flight per warp on a dense term
 #ifndef CCR_BMW_BLOCKS_PER_SM
 #define CCR_BMW_BLOCKS_PER_SM 4
@@ -171,9 +172,10 @@ int launch_bm25_topk_warp(const long long* post_indptr, const int* post_docs, co
                           const int* head_slot, const double* head_rows, long long ld_head,
                           const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
                           u64* cand, int* counts, u32* row_tau, double* dense_out, long long ld_out, cudaStream_t st);
-int launch_bm25_head_slots(const int* head_terms, int n_head, int* head_slot, cudaStream_t st);
+int launch_bm25_head_slots(const int* head_terms, int n_head, long long n_terms, int* head_slot, cudaStream_t st);
 int launch_bm25_head_rows(const long long* post_indptr, const int* post_docs, const double* post_val,
-                          const int* head_terms, int n_head, long long ld_head, double* rows, cudaStream_t st);
+                          const int* head_terms, int n_head, long long n_terms, long long ld_head, double* rows,
+                          cudaStream_t st);
 int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, const float* post_tf, const double* idf,
                         const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
                         cudaStream_t st);

@@ -245,7 +245,8 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
  * cursor, no searches).  ccr_bm25_build_head_rows fills head_slot int32[n_terms] (slot of a head term,
  * -1 for every other term) and head_rows float64[n_head, pitch] with pitch = ccr_bm25_head_row_pitch(n_docs)
  * (n_docs rounded up to the kernel's 512-doc chunk) from the postings of head_terms int32[n_head] (device;
- * distinct term ids chosen by the caller, e.g. every term with df >= n_docs / 4).  The posting lists stay
+ * distinct term ids chosen by the caller, e.g. every term with df >= n_docs / 4; ids outside [0, n_terms)
+ * are ignored).  The posting lists stay
  * complete, so head_slot = head_rows = NULL is always valid (and is what queries of more than 16
  * distinct terms use).
  */
