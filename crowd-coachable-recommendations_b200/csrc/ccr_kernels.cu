@@ -1000,10 +1000,12 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
   __shared__ long long s_end[kBmwWarps][kBmwMaxTerms];
   __shared__ int s_nxt[kBmwWarps][kBmwMaxTerms];   // head terms: -(slot + 1)
   __shared__ u32 s_hist[kBmwWarps][256];
-  __shared__ u32 s_tau_blk;  // ord32 of the best threshold any of the block's streams has reached (same query)
+  __shared__ u32 s_tau_blk;  // ord32 of the best lower bound of the query's k-th best any of the block's streams knows
+  __shared__ u32 s_jth[kBmwWarps];  // per stream: ord32 of a score with >= ceil(k / kBmwSketchM) of its docs at or above it
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long row = blockIdx.y;
   if (threadIdx.x == 0) s_tau_blk = 0u;
+  if (threadIdx.x < kBmwWarps) s_jth[threadIdx.x] = 0u;
   __syncthreads();  // the only block barrier: from here on every warp runs on its own
   const int stream = blockIdx.x * kBmwWarps + warp, n_streams = S * kBmwWarps;
   const long long n_mini = (N + kBmwMini - 1) / kBmwMini;
@@ -1159,11 +1161,29 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
         // buffers fall back to the exact radix select
         u32 pivot_ord = 0u, j_ord = 0u;
         int kept = 0;
-        if (warp_prune_hist<false>(buf, cnt, k, k, (k + C - kBmwMini) / 2, smem_addr(s_hist[warp]), 0u, &pivot_ord, &kept,
-                                   &j_ord)) {
+        if (warp_prune_hist<false>(buf, cnt, k, (k + kBmwSketchM - 1) / kBmwSketchM, (k + C - kBmwMini) / 2,
+                                   smem_addr(s_hist[warp]), 0u, &pivot_ord, &kept, &j_ord)) {
           cnt = kept;
           tau_key = 0ull;
           tau_f = unord32(pivot_ord);
+          // sketch bound: this stream has >= ceil(k/M) docs at or above j_ord; the M-th largest of the block's
+          // published values therefore has >= k docs of the query at or above it
+          if (lane == 0) atomicMax(&s_jth[warp], j_ord);
+          __syncwarp();
+          u32 v = 0u;
+          if (lane < kBmwWarps) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_addr(&s_jth[lane])) : "memory");
+          int gt = 0, ge = 0;
+#pragma unroll
+          for (int i = 0; i < kBmwWarps; ++i) {
+            const u32 o = __shfl_sync(0xffffffffu, v, i);
+            gt += (o > v);
+            ge += (o >= v);
+          }
+          const unsigned who = __ballot_sync(0xffffffffu, lane < kBmwWarps && v != 0u && gt < kBmwSketchM && kBmwSketchM <= ge);
+          if (who) {
+            const u32 bound = __shfl_sync(0xffffffffu, v, __ffs(who) - 1);
+            if (lane == 0) atomicMax(&s_tau_blk, bound);
+          }
         } else {
           const u64 pivot = warp_prune(buf, cnt, k, smem_addr(s_hist[warp]), 0u);
           cnt = k;
@@ -1192,7 +1212,7 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
       __syncwarp();
       jv = (u32)(warp_select_kth(GlobalKeys{buf}, cnt, j, smem_addr(s_hist[warp])) >> 32);
     }
-    __shared__ u32 s_jth[kBmwWarps];
+    __syncthreads();   // (every stream is past its last in-loop use of s_jth)
     if (lane == 0) s_jth[warp] = jv;
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -161,7 +161,7 @@ constexpr int kBmSlack = 1024;     // accumulators ranked between two prune chec
 constexpr int kBmwWarps = 8;
 constexpr int kBmwMini = 512;
 constexpr int kBmwMaxTerms = 16;
-constexpr int kBmwSketchM = 5;       // row bound = the 5th largest of the streams' ceil(k/5)-th best scores
+constexpr int kBmwSketchM = 5;       // query bound = the 5th largest of the streams' ceil(k/5)-th best scores (7, 8: same speed)
 constexpr int kBmwDepth = 4;         // batches of 32 postings in flight per warp on a dense term
 #ifndef CCR_BMW_BLOCKS_PER_SM
 #define CCR_BMW_BLOCKS_PER_SM 4

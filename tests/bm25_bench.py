@@ -136,10 +136,12 @@ def bench_one(head_frac, kern):
 
 def use_lib(path):
     """Builder A/B: switch to another build of libccr_b200 inside this process (same CUDA context)."""
-    global L
+    global L, need, ws
     _lib.LIB_PATH = path
     _lib._lib = None
     L = _lib.lib()
+    need = L.ccr_bm25_topk_workspace_bytes(Q, N, K)   # builds may plan different candidate buffers
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
 
 
 # BM25_LIBS: comma-separated alternative builds of the library to time (default: the in-tree one)
