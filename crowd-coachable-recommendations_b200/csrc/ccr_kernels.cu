@@ -1240,23 +1240,25 @@ __global__ void __launch_bounds__(kBmwWarps * 32, kBmwBlocksPerSm) bm25_topk_war
         asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tb) : "r"(smem_addr(&s_tau_blk)) : "memory");
         if (tb > ord32(tau_f)) { tau_eff = unord32(tb); key_eff = 0ull; }
       }
-      // one max over the lane's 16 docs + one vote: does the mini-chunk hold a candidate at all?
-      float mx = -INFINITY;
+      // one compare per doc, one warp-wide OR: which of the 16 rows of 32 docs hold a candidate at all?
+      // (once the threshold has matured: none, or one or two)
+      unsigned bits = 0u;
 #pragma unroll
-      for (int j = 0; j < kBmwMini / 32; ++j) mx = fmaxf(mx, (float)acc[j * 32 + lane]);
-      if (__any_sync(0xffffffffu, mx >= tau_eff)) {
-        for (int base = 0; base < len; base += 32) {
-          const int j = base + lane;
-          bool pass = false;
-          u64 key = 0ull;
-          if (j < len) {
-            const float sc = (float)acc[j];
-            if (sc >= tau_eff) { key = make_key(sc, (u32)(c0 + j)); pass = key > key_eff; }
-          }
-          const unsigned m = __ballot_sync(0xffffffffu, pass);
-          if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
-          cnt += __popc(m);
+      for (int j = 0; j < kBmwMini / 32; ++j) bits |= ((float)acc[j * 32 + lane] >= tau_eff ? 1u : 0u) << j;
+      unsigned rows = __reduce_or_sync(0xffffffffu, bits);
+      while (rows) {
+        const int j = __ffs(rows) - 1;
+        rows &= rows - 1u;
+        const int idx = j * 32 + lane;
+        bool pass = false;
+        u64 key = 0ull;
+        if (((bits >> j) & 1u) && idx < len) {   // docs beyond N score 0: never candidates
+          key = make_key((float)acc[idx], (u32)(c0 + idx));
+          pass = key > key_eff;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (pass) buf[cnt + __popc(m & ((1u << lane) - 1u))] = key;
+        cnt += __popc(m);
       }
       __syncwarp();
       if (cnt > C - kBmwMini) {  // C >= 2k + kBmwMini: room for the next mini-chunk after a prune
