@@ -778,7 +778,8 @@ int ccr_bm25_topk(const int64_t* post_indptr, const int32_t* post_docs, const do
   if (cudaMemsetAsync(row_tau, 0, (size_t)Bq * sizeof(u32), st) != cudaSuccess) return fail(CCR_ECUDA, "memset bm25 bounds");
   int lr = warp ? launch_bm25_topk_warp(pi, post_docs, post_val, head_slot, head_rows, ccr_bm25_head_row_pitch(n_docs), qi,
                                         q_terms, Bq, n_docs, k, pl.C, pl.S, cand, counts, row_tau, nullptr, 0, st)
-                : launch_bm25_topk(pi, post_docs, post_val, qi, q_terms, Bq, n_docs, k, pl.C, pl.S, cand, counts, nullptr, 0, st);
+                : launch_bm25_topk(pi, post_docs, post_val, head_slot, head_rows, ccr_bm25_head_row_pitch(n_docs), qi, q_terms,
+                                   Bq, n_docs, k, pl.C, pl.S, cand, counts, nullptr, 0, st);
   if (lr) return fail(CCR_ECUDA, "bm25 top-k launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   FinalizeParams fp = {};
   fp.B = (int)Bq; fp.k = k; fp.C = pl.C; fp.S = pl.streams; fp.cand = cand; fp.counts = counts;
@@ -804,7 +805,8 @@ int ccr_bm25_scores_f64(const int64_t* post_indptr, const int32_t* post_docs, co
   int lr = warp ? launch_bm25_topk_warp((const long long*)post_indptr, post_docs, post_val, head_slot, head_rows,
                                         ccr_bm25_head_row_pitch(n_docs), (const long long*)q_indptr,
                                         q_terms, Bq, n_docs, 1, pl.C, pl.S, nullptr, nullptr, nullptr, scores, ld, (cudaStream_t)stream)
-                : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, (const long long*)q_indptr, q_terms,
+                : launch_bm25_topk((const long long*)post_indptr, post_docs, post_val, head_slot, head_rows,
+                                   ccr_bm25_head_row_pitch(n_docs), (const long long*)q_indptr, q_terms,
                                    Bq, n_docs, 1, pl.C, pl.S, nullptr, nullptr, scores, ld, (cudaStream_t)stream);
   if (lr) return fail(CCR_ECUDA, "bm25 scores launch failed: %s", cudaGetErrorString((cudaError_t)lr));
   return CCR_OK;

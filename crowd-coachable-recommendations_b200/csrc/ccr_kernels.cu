@@ -835,6 +835,8 @@ constexpr size_t kBmSmem = (size_t)kBmChunk * 8 + (size_t)kBmMaxTerms * (8 + 8 +
 __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* __restrict__ post_indptr,
                                                                const int* __restrict__ post_docs,
                                                                const double* __restrict__ post_val,
+                                                               const int* __restrict__ head_slot,
+                                                               const double* __restrict__ head_rows, long long ld_head,
                                                                const long long* __restrict__ q_indptr,
                                                                const int* __restrict__ q_terms, long long N, int k,
                                                                int C, int S, u64* cand, int* counts,
@@ -863,6 +865,11 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
   // per-term cursor = first posting with doc >= d0 (one binary search per block and term)
   for (int t = tid; t < T; t += kBmThreads) {
     const int term = q_terms[tb + t];
+    const int slot = head_slot ? __ldg(head_slot + term) : -1;
+    if (slot >= 0) {  // head term: a dense float64 row instead of the list (a passage used as query is full of them)
+      cur[t] = 0; pend[t] = 0; nxt[t] = -(slot + 1);
+      continue;
+    }
     long long lo = post_indptr[term];
     const long long end = post_indptr[term + 1];
     long long hi = end;
@@ -880,7 +887,14 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
     for (int j = tid; j < kBmChunk; j += kBmThreads) acc[j] = 0.0;
     __syncthreads();
     for (int t = 0; t < T; ++t) {
-      if ((long long)nxt[t] >= c1) continue;  // uniform: shared-memory value
+      const int nx = nxt[t];
+      if ((long long)nx >= c1) continue;  // uniform: shared-memory value
+      if (nx < 0) {   // head term: coalesced adds of its dense row (x + 0.0 == x where the doc lacks the term)
+        const double* r = head_rows + (long long)(-nx - 1) * ld_head + c0;
+        for (int j = tid; j < len; j += kBmThreads) acc[j] += __ldg(r + j);
+        __syncthreads();
+        continue;
+      }
       long long e = cur[t];
       const long long end = pend[t];
       bool more = true;
@@ -969,14 +983,15 @@ __global__ void __launch_bounds__(kBmThreads) bm25_topk_kernel(const long long* 
 }
 
 int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const double* post_val,
+                     const int* head_slot, const double* head_rows, long long ld_head,
                      const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
                      u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st) {
   if (Bq <= 0 || N <= 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(bm25_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBmSmem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid((unsigned)S, (unsigned)Bq);
-  bm25_topk_kernel<<<grid, kBmThreads, kBmSmem, st>>>(post_indptr, post_docs, post_val, q_indptr, q_terms, N, k, C, S,
-                                                     cand, counts, dense_out, ld_out);
+  bm25_topk_kernel<<<grid, kBmThreads, kBmSmem, st>>>(post_indptr, post_docs, post_val, head_slot, head_rows, ld_head,
+                                                     q_indptr, q_terms, N, k, C, S, cand, counts, dense_out, ld_out);
   return (int)cudaGetLastError();
 }
 

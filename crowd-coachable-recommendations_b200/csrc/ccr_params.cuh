@@ -180,7 +180,7 @@ int launch_bm25_impacts(const long long* post_indptr, const int* post_docs, cons
                         const double* doc_norm, double k1p1, long long V, long long nnz, double* val,
                         cudaStream_t st);
 int launch_bm25_topk(const long long* post_indptr, const int* post_docs, const double* post_val,
-                     const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
+                     const int* head_slot, const double* head_rows, long long ld_head, const long long* q_indptr, const int* q_terms, long long Bq, long long N, int k, int C, int S,
                      u64* cand, int* counts, double* dense_out, long long ld_out, cudaStream_t st);
 
 }  // namespace ccr

@@ -247,8 +247,7 @@ int ccr_topk_dense_f32(const float* scores, int64_t B, int64_t n_cols, int64_t l
  * (n_docs rounded up to the kernel's 512-doc chunk) from the postings of head_terms int32[n_head] (device;
  * distinct term ids chosen by the caller, e.g. every term with df >= n_docs / 4; ids outside [0, n_terms)
  * are ignored).  The posting lists stay
- * complete, so head_slot = head_rows = NULL is always valid (and is what queries of more than 16
- * distinct terms use).
+ * complete, so head_slot = head_rows = NULL is always valid.
  */
 int64_t ccr_bm25_head_row_pitch(int64_t n_docs);
 int ccr_bm25_build_head_rows(const int64_t* post_indptr, const int32_t* post_docs, const double* post_val,

@@ -118,15 +118,18 @@ def test_bm25_dense_scores_vs_oracle_many_chunks(ccr):
 
 def test_bm25_head_rows_bit_identical(ccr):
     """Dense float64 rows for the head terms (hybrid index) change the memory traffic, not a single bit of
-    the scores: postings only == default fraction == nearly every term dense, on the warp-private kernel
-    (short queries) with n_docs not a multiple of the 512-doc chunk."""
+    the scores: postings only == default fraction == nearly every term dense, on both kernels (the batch
+    holds short queries and a whole passage) with n_docs not a multiple of the 512-doc chunk."""
     corpus, queries = _synthetic(17, 33333, 64, vocab=300, doc_len=40)
-    queries = [q for q in queries if len(set(q.split())) <= 16]
-    assert len(queries) >= 20
+    queries.append(" ".join(corpus[i] for i in (3, 11, 12, 40, 41)))   # a long query: block-wide kernel
+    n_terms = [len(set(q.split())) for q in queries]
+    assert sum(n <= 16 for n in n_terms) >= 20 and max(n_terms) > 16
+    short = [q for q, n in zip(queries, n_terms) if n <= 16]
     model = ccr.BM25(b=0.75, k1=1.2, head_df_fraction=None).fit(corpus)
     assert model.head_terms().size == 0
-    want = model.scores(queries).cpu().numpy()
-    ws, wi = model.topk(queries, 1001)
+    want = model.scores(queries).cpu().numpy()          # longest query > 16 terms: block-wide kernel
+    want_short = model.scores(short).cpu().numpy()      # warp-private kernel
+    ws, wi = model.topk(queries, 1001)                  # short / long queries split between the two
     ref = O.BM25Ref(b=0.75, k1=1.2).fit(corpus)
     np.testing.assert_array_equal(want[3], ref.transform(queries[3]))
     sizes = []
@@ -137,6 +140,7 @@ def test_bm25_head_rows_bit_identical(ccr):
         sizes.append(model.head_terms().size)
         assert model._head_rows is not None and model._head_rows.shape[0] == sizes[-1]
         np.testing.assert_array_equal(got, want)
+        np.testing.assert_array_equal(model.scores(short).cpu().numpy(), want_short)
         s, i = model.topk(queries, 1001)
         assert torch.equal(s, ws) and torch.equal(i, wi)
     assert 0 < sizes[0] <= sizes[1] <= sizes[2] == 64  # capped at HEAD_MAX_TERMS
