@@ -1433,16 +1433,38 @@ __global__ void __launch_bounds__(kDenseThreads) select_dense_kernel(const float
   const float* r = scores + row * ld;
   if (tid == 0) { s_cnt = 0; s_tau_f = -INFINITY; s_tau_key = 0ull; }
   __syncthreads();
+  // kDenseSlack columns per iteration: 16 per thread as four 16-byte loads in flight (scalar loads at a
+  // ragged end or an unaligned row), one max + ONE block vote, and only an iteration that holds a
+  // candidate pays for the appends, the second barrier and the prune check.
+  const bool vec = ((uintptr_t)r & 15) == 0;
+  constexpr int kPer = kDenseSlack / kDenseThreads;   // 16
   for (long long base = i0; base < i1; base += kDenseSlack) {
+    float v[kPer];
+    if (vec && base + kDenseSlack <= i1) {
 #pragma unroll
-    for (int j = 0; j < kDenseSlack / kDenseThreads; ++j) {
-      const long long i = base + j * kDenseThreads + tid;
-      if (i < i1) {
-        const float sc = __ldg(r + i);
-        if (sc >= s_tau_f) {  // NaN scores never rank (torch would put them first; the reference has none)
-          const u64 key = make_key(sc, (u32)i);
-          if (key > s_tau_key) buf[atomicAdd(&s_cnt, 1)] = key;
-        }
+      for (int q = 0; q < kPer / 4; ++q) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(r + base) + q * kDenseThreads + tid);
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const long long i = base + ((j >> 2) * kDenseThreads + tid) * 4 + (j & 3);
+        v[j] = i < i1 ? __ldg(r + i) : __uint_as_float(0x7fc00000u);   // NaN: fails every >= test
+      }
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int j = 1; j < kPer; ++j) mx = fmaxf(mx, v[j]);   // NaN scores never rank (torch would put them first; the reference has none)
+    const float tau_f = s_tau_f;
+    const u64 tau_key = s_tau_key;
+    if (!__syncthreads_or(mx >= tau_f)) continue;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      if (v[j] >= tau_f) {
+        const long long i = base + ((j >> 2) * kDenseThreads + tid) * 4 + (j & 3);
+        const u64 key = make_key(v[j], (u32)i);
+        if (key > tau_key) buf[atomicAdd(&s_cnt, 1)] = key;
       }
     }
     __syncthreads();

@@ -137,7 +137,7 @@ int launch_first_hit_rank(const long long* ids, long long B, int k, const long l
                           int* out_rank, cudaStream_t st);
 
 // dense top-k (ccr_kernels.cu)
-constexpr int kDenseSlack = 1024;  // columns one block scans between two prune checks
+constexpr int kDenseSlack = 4096;  // columns one block scans between two prune checks (16 per thread)
 int launch_select_dense(const float* scores, long long ld, long long B, long long N, int k, int k_keep,
                         const long long* mask_indptr, int C, int S, u64* cand, int* counts, cudaStream_t st);
 int launch_override_dense(const float* scores, long long ld, int B, long long N, const long long* mask_indptr,
