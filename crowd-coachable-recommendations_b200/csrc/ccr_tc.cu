@@ -14,6 +14,7 @@
 // Persistent: grid = #SMs, each CTA walks units (query tile, item split) round-robin with the
 // query tile varying fastest so CTAs running concurrently share item tiles through L2.
 #include <cuda.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -56,6 +57,10 @@ struct __align__(8) TcShared {
   u32 hist[kEpiWarps][256];
   u64 stage[kEpiWarps][kStageKeys];
 };
+// the store epilogue (kMode 2) carves 4 KB per warp out of hist + stage, which it does not use otherwise
+static_assert(offsetof(TcShared, stage) == offsetof(TcShared, hist) + sizeof(u32) * kEpiWarps * 256 &&
+                  sizeof(u32) * kEpiWarps * 256 + sizeof(u64) * kEpiWarps * kStageKeys >= (size_t)kEpiWarps * 4096,
+              "TcShared: hist and stage must form one block of >= 4 KB per selection warp");
 constexpr size_t kTcSmemBytes = (size_t)4 * (kBytesA + kBytesB) + sizeof(TcShared) + 1024;  // same for both geometries
 
 // ---------------------------------------------------------------------------------------
@@ -677,18 +682,31 @@ select_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
               for (int g = 0; g < 4; ++g) m8[g] = (cc + 8 * g + 8 <= p.n_items) ? max8(v, g) : -INFINITY;
               *reinterpret_cast<float4*>(orow + (cc >> 3)) = make_float4(m8[0], m8[1], m8[2], m8[3]);
             }
-          } else if (valid_row) {
-            if (vec_ok && cc + 32 <= p.n_items) {
-              float4* o4 = reinterpret_cast<float4*>(orow + cc);
+          } else if (vec_ok && cc + 32 <= p.n_items) {   // warp-uniform
+            // The lane holds 32 columns of ITS row: stored as they are, one instruction would touch 32 rows
+            // (0.5 TB/s measured).  Transpose the 32 x 32 block through this warp's 4 KB of shared memory
+            // (16-byte chunks XOR-swizzled by the row: conflict-free both ways) so that one instruction
+            // writes 4 rows x 128 contiguous bytes.
+            float* ts = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sh->hist) + warp * 4096);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                o4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                    __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            } else {
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(ts + lane * 32 + ((q ^ (lane & 7)) << 2)) =
+                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                              __uint_as_float(v[4 * q + 3]));
+            __syncwarp();
+            const int q = lane & 7;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cc + j < p.n_items) orow[cc + j] = __uint_as_float(v[j]);
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + (lane >> 3);
+              const float4 x = *reinterpret_cast<const float4*>(ts + rr * 32 + ((q ^ (rr & 7)) << 2));
+              const int grow = qt * kQRows + crank * kQTile + quad * 32 + rr;
+              if (grow < p.B) *reinterpret_cast<float4*>(p.dense_out + (long long)grow * p.ld_out + cc + q * 4) = x;
             }
+            __syncwarp();
+          } else if (valid_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cc + j < p.n_items) orow[cc + j] = __uint_as_float(v[j]);
           }
         }
         tc_fence_before();
