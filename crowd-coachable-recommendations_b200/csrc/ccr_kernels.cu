@@ -1470,8 +1470,18 @@ __global__ void __launch_bounds__(kDenseThreads) select_dense_kernel(const float
     __syncthreads();
     if (s_cnt > C - kDenseSlack) {  // uniform: read after the barrier; C >= 2 * k_row + slack
       if (tid < 32) {
-        const u64 pivot = warp_prune(buf, s_cnt, k_row, smem_addr(s_hist), 0u);
-        if (tid == 0) { s_cnt = k_row; s_tau_key = pivot; s_tau_f = key_score(pivot); }
+        // one histogram pass first (a score threshold with >= k_row candidates at or above it is all the
+        // stream needs); the exact radix select only for tie-heavy or crowded buffers
+        u32 pivot_ord = 0u, j_ord = 0u;
+        int kept = 0;
+        const int n_now = s_cnt;
+        if (warp_prune_hist<false>(buf, n_now, k_row, k_row, (k_row + C - kDenseSlack) / 2, smem_addr(s_hist), 0u,
+                                   &pivot_ord, &kept, &j_ord)) {
+          if (tid == 0) { s_cnt = kept; s_tau_key = 0ull; s_tau_f = unord32(pivot_ord); }
+        } else {
+          const u64 pivot = warp_prune(buf, n_now, k_row, smem_addr(s_hist), 0u);
+          if (tid == 0) { s_cnt = k_row; s_tau_key = pivot; s_tau_f = key_score(pivot); }
+        }
       }
     }
     __syncthreads();
