@@ -1,7 +1,8 @@
 // Whole-matrix argsort (rime_lite `_argsort`, src/rime_lite/util/__init__.py:158-184) and the MRR
 // first-hit scan (scripts/al_0_rank.py:130-133) -- HBM-bound integer work, CUDA cores only.
 //
-//   argsort : keys = ~ord64(double(score) [+ prior | := value]) per matrix element, payload = flat
+//   argsort : keys = ~ord64(double(score) [+ prior | := value]) per matrix element (~ord32(score) when no prior
+//             is given: the same order in half the bytes and passes), payload = flat
 //             index; LSD radix sort, 8 passes of 8 bits, each pass = per-tile digit histogram ->
 //             exclusive scan over (digit, tile) -> stable scatter (skipped on the device when every key
 //             carries the same digit).  Ascending ~ord64 == descending
@@ -30,17 +31,24 @@ __device__ __forceinline__ u32 sort_needed_passes(u64 key) {
   return m | 0x80u;   // the top pass always runs
 }
 
+template <typename K>
 __global__ void __launch_bounds__(256) sort_build_keys_kernel(const float* __restrict__ scores, long long B, long long N,
-                                                              long long ld, u64* __restrict__ keys,
+                                                              long long ld, K* __restrict__ keys,
                                                               u32* __restrict__ payload, int* __restrict__ state) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   u32 need = 0;
   if (i < B * N) {
     const long long r = i / N, c = i - r * N;
-    const u64 key = ~ord64((double)scores[r * ld + c]);
-    keys[i] = key;
+    const float sc = scores[r * ld + c];
     payload[i] = (u32)i;
-    need = sort_needed_passes(key);
+    if (sizeof(K) == 4) {   // no float64 prior anywhere: the float32 order is the order
+      keys[i] = (K)~ord32(sc);
+      need = 0xFu;
+    } else {
+      const u64 key = ~ord64((double)sc);
+      keys[i] = (K)key;
+      need = sort_needed_passes(key);
+    }
   }
   need = __reduce_or_sync(0xffffffffu, need);
   if ((threadIdx.x & 31) == 0 && (need & ~(u32)state[3])) atomicOr(state + 3, (int)need);
@@ -69,19 +77,20 @@ __global__ void __launch_bounds__(256) sort_override_keys_kernel(const float* __
 // Pass state on the device (no host round trip): state[0] = which buffer holds the current order (0: a,
 // 1: b), state[1] = skip flag of the pass in flight, state[3] = mask of the passes that can change the
 // order (sort_needed_passes; 3 of the 8 passes are no-ops when no float64 prior is involved).
-struct SortBufs {
-  u64* k[2];
+template <typename K> struct SortBufs {
+  K* k[2];
   u32* p[2];
 };
 
 // per-tile digit counts, stored digit-major: hist[d * n_tiles + tile]
-__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortBufs bufs, const int* __restrict__ state,
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads) sort_hist_kernel(SortBufs<K> bufs, const int* __restrict__ state,
                                                                  long long n, int shift, u32* __restrict__ hist,
                                                                  int n_tiles) {
   if (!((state[3] >> (shift >> 3)) & 1)) return;   // pass not needed: nobody reads its counts
   __shared__ u32 s_cnt[256];
   const int tid = threadIdx.x;
-  const u64* __restrict__ keys = bufs.k[state[0]];
+  const K* __restrict__ keys = bufs.k[state[0]];
   s_cnt[tid] = 0;
   __syncthreads();
   const long long base = (long long)blockIdx.x * kSortTile;
@@ -146,20 +155,21 @@ __global__ void sort_flip_kernel(int* __restrict__ state) {
 // written out position by position, so that consecutive threads write consecutive addresses inside every
 // digit's run (a random digit scatters 32 lanes to 32 runs otherwise: 2x DRAM write amplification and
 // 1.98 ms per pass for 67 M keys instead of the 0.8 ms measured with the reorder).
-constexpr size_t kSortScatterSmem = (size_t)kSortTile * (sizeof(u64) + sizeof(u32));
+template <typename K> constexpr size_t sort_scatter_smem() { return (size_t)kSortTile * (sizeof(K) + sizeof(u32)); }
 
-__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs bufs, const int* __restrict__ state,
+template <typename K>
+__global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs<K> bufs, const int* __restrict__ state,
                                                                     long long n, int shift,
                                                                     const u32* __restrict__ hist,
                                                                     const u32* __restrict__ dbase, int n_tiles) {
   if (state[1]) return;   // the pass cannot change the order (see sort_scan_digits_kernel)
   const int src = state[0];
-  const u64* __restrict__ keys_in = bufs.k[src];
+  const K* __restrict__ keys_in = bufs.k[src];
   const u32* __restrict__ pay_in = bufs.p[src];
-  u64* __restrict__ keys_out = bufs.k[src ^ 1];
+  K* __restrict__ keys_out = bufs.k[src ^ 1];
   u32* __restrict__ pay_out = bufs.p[src ^ 1];
   extern __shared__ __align__(16) unsigned char sort_smem[];
-  u64* s_key = reinterpret_cast<u64*>(sort_smem);                 // [kSortTile] the tile, digit-major
+  K* s_key = reinterpret_cast<K*>(sort_smem);                     // [kSortTile] the tile, digit-major
   u32* s_pay = reinterpret_cast<u32*>(s_key + kSortTile);         // [kSortTile]
   __shared__ u32 s_base[256];                      // global offset of this tile's first key of each digit
   __shared__ u32 s_toff[256];                      // tile-local offset of each digit's run
@@ -172,13 +182,13 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs buf
   __syncthreads();
   const long long tile0 = (long long)blockIdx.x * kSortTile;
   const long long base = tile0 + (long long)warp * (32 * kSortPerThread);
-  u64 key[kSortPerThread];
+  K key[kSortPerThread];
   u32 pay[kSortPerThread], rank[kSortPerThread];
 #pragma unroll
   for (int j = 0; j < kSortPerThread; ++j) {
     const long long i = base + j * 32 + lane;
     const bool live = i < n;
-    key[j] = live ? keys_in[i] : 0ull;
+    key[j] = live ? keys_in[i] : (K)0;
     pay[j] = live ? pay_in[i] : 0u;
   }
 #pragma unroll
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs buf
   __syncthreads();
   const int tile_n = (int)((n - tile0 < (long long)kSortTile) ? (n - tile0) : (long long)kSortTile);
   for (int i = tid; i < tile_n; i += kSortThreads) {
-    const u64 k2 = s_key[i];
+    const K k2 = s_key[i];
     const u32 d = (u32)(k2 >> shift) & 255u;
     const u32 pos = s_base[d] + ((u32)i - s_toff[d]);
     keys_out[pos] = k2;
@@ -229,12 +239,13 @@ __global__ void __launch_bounds__(kSortThreads) sort_scatter_kernel(SortBufs buf
   }
 }
 
-__global__ void __launch_bounds__(256) sort_unravel_kernel(SortBufs bufs, const int* __restrict__ state, long long n,
+__global__ void __launch_bounds__(256) sort_unravel_kernel(const u32* __restrict__ pay0, const u32* __restrict__ pay1,
+                                                           const int* __restrict__ state, long long n,
                                                            long long N, long long* __restrict__ out_rows,
                                                            long long* __restrict__ out_cols) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const u32 flat = bufs.p[state[0]][i];   // n = B * N < 2^32 (checked by the caller), so N fits 32 bits too
+  const u32 flat = (state[0] ? pay1 : pay0)[i];   // n = B * N < 2^32 (checked by the caller), so N fits 32 bits too
   const u32 r = flat / (u32)N;
   out_rows[i] = (long long)r;
   out_cols[i] = (long long)(flat - r * (u32)N);
@@ -251,6 +262,31 @@ size_t argsort_workspace_bytes(long long n) {
   off = up(off + (size_t)256 * (size_t)(tiles > 0 ? tiles : 1) * 4);   // per-tile digit counts
   off = up(off + (size_t)(256 + 256 + 4) * 4);                          // digit totals, digit bases, pass state
   return off;
+}
+
+template <typename K>
+static int sort_passes(SortBufs<K> bufs, long long n, int tiles, u32* hist, u32* totals, u32* dbase, int* state,
+                       cudaStream_t st) {
+  {
+    static bool attr_done[64];  // per function and device: dynamic + 10 KB of static shared memory exceed 48 KB
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = -1; }
+    if (dev < 0 || !attr_done[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(sort_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sort_scatter_smem<K>());
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0) attr_done[dev] = true;
+    }
+  }
+  for (int pass = 0; pass < (int)sizeof(K); ++pass) {
+    const int shift = pass * 8;
+    sort_hist_kernel<K><<<tiles, kSortThreads, 0, st>>>(bufs, state, n, shift, hist, tiles);
+    sort_scan_rows_kernel<<<256, 1024, 0, st>>>(hist, tiles, totals);
+    sort_scan_digits_kernel<<<1, 256, 0, st>>>(totals, pass, dbase, state);
+    sort_scatter_kernel<K><<<tiles, kSortThreads, sort_scatter_smem<K>(), st>>>(bufs, state, n, shift, hist, dbase, tiles);
+    sort_flip_kernel<<<1, 1, 0, st>>>(state);
+  }
+  return (int)cudaGetLastError();
 }
 
 int launch_argsort(const float* scores, long long B, long long N, long long ld, const long long* indptr, const int* cols,
@@ -270,33 +306,24 @@ int launch_argsort(const float* scores, long long B, long long N, long long ld, 
   u32* totals = (u32*)(w + off);
   u32* dbase = totals + 256;
   int* state = (int*)(dbase + 256);
-  SortBufs bufs;
-  bufs.k[0] = ka; bufs.k[1] = kb; bufs.p[0] = pa; bufs.p[1] = pb;
   const unsigned gb = (unsigned)((n + 255) / 256);
   if (cudaMemsetAsync(state, 0, 4 * sizeof(int), st) != cudaSuccess) return (int)cudaGetLastError();
-  {
-    static bool attr_done[64];  // per function and device: 48 KB of dynamic + 10 KB of static shared memory
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); dev = -1; }
-    if (dev < 0 || !attr_done[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(sort_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortScatterSmem);
-      if (e != cudaSuccess) return (int)e;
-      if (dev >= 0) attr_done[dev] = true;
-    }
-  }
-  sort_build_keys_kernel<<<gb, 256, 0, st>>>(scores, B, N, ld, ka, pa, state);
-  if (nnz > 0 && indptr)
+  if (nnz > 0 && indptr) {   // float64 priors decide: 64-bit keys, 8 passes
+    SortBufs<u64> bufs;
+    bufs.k[0] = ka; bufs.k[1] = kb; bufs.p[0] = pa; bufs.p[1] = pb;
+    sort_build_keys_kernel<u64><<<gb, 256, 0, st>>>(scores, B, N, ld, ka, pa, state);
     sort_override_keys_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(scores, B, N, ld, indptr, cols, vals, mode, ka,
                                                                           state);
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = pass * 8;
-    sort_hist_kernel<<<tiles, kSortThreads, 0, st>>>(bufs, state, n, shift, hist, tiles);
-    sort_scan_rows_kernel<<<256, 1024, 0, st>>>(hist, tiles, totals);
-    sort_scan_digits_kernel<<<1, 256, 0, st>>>(totals, pass, dbase, state);
-    sort_scatter_kernel<<<tiles, kSortThreads, kSortScatterSmem, st>>>(bufs, state, n, shift, hist, dbase, tiles);
-    sort_flip_kernel<<<1, 1, 0, st>>>(state);
+    const int rc = sort_passes<u64>(bufs, n, tiles, hist, totals, dbase, state, st);
+    if (rc) return rc;
+  } else {   // the float32 order is the order: 32-bit keys (in the first halves of the key buffers), 4 passes
+    SortBufs<u32> bufs;
+    bufs.k[0] = reinterpret_cast<u32*>(ka); bufs.k[1] = reinterpret_cast<u32*>(kb); bufs.p[0] = pa; bufs.p[1] = pb;
+    sort_build_keys_kernel<u32><<<gb, 256, 0, st>>>(scores, B, N, ld, bufs.k[0], pa, state);
+    const int rc = sort_passes<u32>(bufs, n, tiles, hist, totals, dbase, state, st);
+    if (rc) return rc;
   }
-  sort_unravel_kernel<<<gb, 256, 0, st>>>(bufs, state, n, N, out_rows, out_cols);
+  sort_unravel_kernel<<<gb, 256, 0, st>>>(pa, pb, state, n, N, out_rows, out_cols);
   return (int)cudaGetLastError();
 }
 
