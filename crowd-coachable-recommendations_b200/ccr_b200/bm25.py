@@ -20,7 +20,7 @@ from .engine import _require_cuda, _stream_ptr, workspace  # noqa: F401
 
 RANKING_TOPN = 1001  # scripts/ms_marco_eval.py:182
 QUERY_CHUNK = 4096   # queries per fused call
-WARP_KERNEL_MAX_TERMS = 16  # libccr_b200: kBmwMaxTerms
+WARP_KERNEL_MAX_TERMS = 32  # libccr_b200: kBmwMaxTerms
 MAX_QUERY_TERMS = 512
 HEAD_DF_FRACTION = 0.25     # terms present in at least this share of the docs also get a dense float64 row
 HEAD_MAX_TERMS = 64

@@ -157,10 +157,10 @@ constexpr int kBmThreads = CCR_BM_THREADS;
 constexpr int kBmBlocksPerSm = CCR_BM_BLOCKS_PER_SM;
 constexpr int kBmMaxTerms = 512;   // distinct vocabulary terms per query
 constexpr int kBmSlack = 1024;     // accumulators ranked between two prune checks
-// warp-private variant: 8 independent warps per block, 512-doc mini-chunks, <= 16 distinct query terms
+// warp-private variant: 8 independent warps per block, 512-doc mini-chunks, <= 32 distinct query terms
 constexpr int kBmwWarps = 8;
 constexpr int kBmwMini = 512;
-constexpr int kBmwMaxTerms = 16;
+constexpr int kBmwMaxTerms = 32;   // one lane per term
 constexpr int kBmwSketchM = 5;       // query bound = the 5th largest of the streams' ceil(k/5)-th best scores (7, 8: same speed)
 constexpr int kBmwDepth = 4;         // batches of 32 postings in flight per warp on a dense term
 #ifndef CCR_BMW_BLOCKS_PER_SM

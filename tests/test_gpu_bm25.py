@@ -75,7 +75,7 @@ def _synthetic(seed, n, q, vocab, doc_len):
 
 @pytest.fixture(params=["auto", "blockwide"])
 def bm25_kernel(request):
-    """auto: queries of <= 16 distinct terms take the warp-private kernel, longer ones the block-wide
+    """auto: queries of <= 32 distinct terms take the warp-private kernel, longer ones the block-wide
     kernel (the batches below hold both kinds); blockwide: everything on the block-wide kernel."""
     from ccr_b200 import _lib
 
@@ -121,13 +121,13 @@ def test_bm25_head_rows_bit_identical(ccr):
     the scores: postings only == default fraction == nearly every term dense, on both kernels (the batch
     holds short queries and a whole passage) with n_docs not a multiple of the 512-doc chunk."""
     corpus, queries = _synthetic(17, 33333, 64, vocab=300, doc_len=40)
-    queries.append(" ".join(corpus[i] for i in (3, 11, 12, 40, 41)))   # a long query: block-wide kernel
+    queries.append(" ".join(corpus[i] for i in range(3, 15)))   # a long query: block-wide kernel
     n_terms = [len(set(q.split())) for q in queries]
-    assert sum(n <= 16 for n in n_terms) >= 20 and max(n_terms) > 16
-    short = [q for q, n in zip(queries, n_terms) if n <= 16]
+    assert sum(n <= 32 for n in n_terms) >= 20 and max(n_terms) > 32
+    short = [q for q, n in zip(queries, n_terms) if n <= 32]
     model = ccr.BM25(b=0.75, k1=1.2, head_df_fraction=None).fit(corpus)
     assert model.head_terms().size == 0
-    want = model.scores(queries).cpu().numpy()          # longest query > 16 terms: block-wide kernel
+    want = model.scores(queries).cpu().numpy()          # longest query > 32 terms: block-wide kernel
     want_short = model.scores(short).cpu().numpy()      # warp-private kernel
     ws, wi = model.topk(queries, 1001)                  # short / long queries split between the two
     ref = O.BM25Ref(b=0.75, k1=1.2).fit(corpus)
